@@ -1,0 +1,542 @@
+// HBM-bound passes of the CartNet layer: edge featuriser, BatchNorm statistics, the gate /
+// aggregate edge pass with its deterministic per-destination reduction, the node update, and the
+// matching backward passes. Replaces the eager elementwise / scatter chains of
+// /root/reference/models/cartnet.py:230-274 and models/utils.py:56-61,87-91.
+//
+// Layout: every [rows, C] tensor is row-major; a row is covered by C/4 consecutive threads with one
+// 128-bit access each (C = 256 -> 64 threads read 1 KB contiguous). Reductions over rows use fp64
+// accumulators in a fixed order: per-thread over a strided row set, then over row-lanes in shared
+// memory, then over blocks in a second launch -- no atomics anywhere, results are reproducible.
+#include "common.cuh"
+
+namespace cartnet {
+
+constexpr int kRedBlocksMax = 4 * kNumSMs;   // 592 partial rows at most
+
+struct BnCoef {   // y = x * scale + shift ; xhat = (x - mean) * rstd
+    float4 mean, rstd, scale, shift;
+};
+__device__ __forceinline__ BnCoef bn_coef(const float* mean, const float* var, const float* w, const float* b,
+                                          float eps, int col) {
+    BnCoef c;
+    float4 m = *reinterpret_cast<const float4*>(mean + col);
+    float4 v = *reinterpret_cast<const float4*>(var + col);
+    float4 ww = w ? *reinterpret_cast<const float4*>(w + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 bb = b ? *reinterpret_cast<const float4*>(b + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    c.mean = m;
+    c.rstd = make_float4(1.0f / sqrtf(v.x + eps), 1.0f / sqrtf(v.y + eps), 1.0f / sqrtf(v.z + eps), 1.0f / sqrtf(v.w + eps));
+    c.scale = make_float4(ww.x * c.rstd.x, ww.y * c.rstd.y, ww.z * c.rstd.z, ww.w * c.rstd.w);
+    c.shift = bb;
+    return c;
+}
+// BN(x) = (x - mean) * (w * rstd) + b   (same association as ATen's batch_norm CPU kernel: alpha*x+beta form
+// differs only in the last ulp; the parity budget is 1e-5)
+__device__ __forceinline__ float4 bn_apply(const BnCoef& c, float4 x) {
+    return make_float4((x.x - c.mean.x) * c.scale.x + c.shift.x, (x.y - c.mean.y) * c.scale.y + c.shift.y,
+                       (x.z - c.mean.z) * c.scale.z + c.shift.z, (x.w - c.mean.w) * c.scale.w + c.shift.w);
+}
+__device__ __forceinline__ float4 bn_hat(const BnCoef& c, float4 x) {
+    return make_float4((x.x - c.mean.x) * c.rstd.x, (x.y - c.mean.y) * c.rstd.y, (x.z - c.mean.z) * c.rstd.z,
+                       (x.w - c.mean.w) * c.rstd.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic column reduction: F(row, col) -> two float4 contributions (a, b); partial[blk][2][C] fp64
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partial) {
+    extern __shared__ double sm[];   // [lanes][2][C]
+    const int tpr = C >> 2;                  // threads per row
+    const int lanes = 256 / tpr;             // row lanes per block
+    const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * 4;
+    const int64_t per_block = ceil_div64(rows, gridDim.x);
+    const int64_t r0 = blockIdx.x * per_block;
+    const int64_t r1 = (r0 + per_block < rows) ? r0 + per_block : rows;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+        float4 va, vb;
+        f(r, col, va, vb);
+        a[0] += (double)va.x; a[1] += (double)va.y; a[2] += (double)va.z; a[3] += (double)va.w;
+        b[0] += (double)vb.x; b[1] += (double)vb.y; b[2] += (double)vb.z; b[3] += (double)vb.w;
+    }
+    double* mine = sm + (size_t)rl * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mine[col + j] = a[j];
+        mine[C + col + j] = b[j];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * C; j += 256) {
+        double s = 0;
+        for (int l = 0; l < lanes; ++l) s += sm[(size_t)l * 2 * C + j];
+        partial[(size_t)blockIdx.x * 2 * C + j] = s;
+    }
+}
+
+enum { FIN_STATS = 0, FIN_SUMS = 1 };
+// FIN_STATS: mean/var (+ running update) from (sum, sumsq); FIN_SUMS: out[0:C]=sum a, out[C:2C]=sum b (ncols_out)
+__global__ void colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, int64_t rows, int mode,
+                                       float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ run_mean,
+                                       float* __restrict__ run_var, float momentum, int n_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == FIN_STATS) {
+        if (c >= C) return;
+        double s = 0, q = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            s += partial[(size_t)b * 2 * C + c];
+            q += partial[(size_t)b * 2 * C + C + c];
+        }
+        const double n = (double)rows;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0) var = 0;
+        out0[c] = (float)mean;
+        out1[c] = (float)var;
+        if (run_mean) {
+            const double unb = rows > 1 ? var * n / (n - 1.0) : var;
+            run_mean[c] = (float)((1.0 - (double)momentum) * (double)run_mean[c] + (double)momentum * mean);
+            run_var[c] = (float)((1.0 - (double)momentum) * (double)run_var[c] + (double)momentum * unb);
+        }
+    } else {
+        if (c >= n_out) return;
+        double s = 0;
+        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2 * C + c];
+        out0[c] = (float)s;
+    }
+}
+
+static inline bool colreduce_shape_ok(int C) {
+    int tpr = C / 4;
+    return C % 4 == 0 && tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0;
+}
+static inline int colreduce_blocks(int64_t rows, int C) {
+    int lanes = 256 / (C / 4);
+    int64_t b = ceil_div64(rows, (int64_t)lanes * 16);
+    if (b > kRedBlocksMax) b = kRedBlocksMax;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <class F>
+static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, float* out0, float* out1, float* rm,
+                         float* rv, float momentum, int n_out, cudaStream_t st) {
+    const int nb = colreduce_blocks(rows, C);
+    const int lanes = 256 / (C / 4);
+    const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
+    colreduce_kernel<F><<<nb, 256, smem, st>>>(f, rows, C, partial);
+    CN_LAUNCH_CHECK();
+    const int nthreads = mode == FIN_STATS ? C : n_out;
+    colreduce_final_kernel<<<ceil_div(nthreads, 128), 128, 0, st>>>(partial, nb, C, rows, mode, out0, out1, rm, rv,
+                                                                   momentum, n_out);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- functors ---------------------------------------------------------------------------
+struct StatsF {
+    const float* x; int64_t ld;
+    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+        a = *reinterpret_cast<const float4*>(x + r * ld + col);
+        b = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
+    }
+};
+template <typename TX>
+struct SumF {
+    const TX* x; int64_t ld;
+    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+        a = load4<TX>(x + r * ld + col);
+        b = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+};
+struct NodeBwdF {
+    const float* dx; const float* m; int D;
+    const float *mean, *var, *w, *bias; float eps;
+    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+        BnCoef c = bn_coef(mean, var, w, bias, eps, col);
+        float4 mm = *reinterpret_cast<const float4*>(m + r * D + col);
+        float4 g = *reinterpret_cast<const float4*>(dx + r * D + col);
+        float4 y = bn_apply(c, mm), h = bn_hat(c, mm);
+        a = make_float4(g.x * dsiluf_(y.x), g.y * dsiluf_(y.y), g.z * dsiluf_(y.z), g.w * dsiluf_(y.w));
+        b = make_float4(a.x * h.x, a.y * h.y, a.z * h.z, a.w * h.w);
+    }
+};
+template <typename T>
+struct EdgeBwdF {
+    const float *g, *s, *dist; const int32_t* dst; const float *de, *dm; int D;
+    const float *mean, *var, *w, *bias; float eps, radius; int use_env;
+    T* ds_t; float* dghat;
+    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+        BnCoef c = bn_coef(mean, var, w, bias, eps, col);
+        const float env = use_env ? cosine_cutoff(dist[r], radius) : 1.0f;
+        const int64_t o = r * D + col;
+        float4 gg = *reinterpret_cast<const float4*>(g + o);
+        float4 ss = *reinterpret_cast<const float4*>(s + o);
+        float4 dd = *reinterpret_cast<const float4*>(de + o);
+        float4 dmd = *reinterpret_cast<const float4*>(dm + (int64_t)dst[r] * D + col);
+        float4 gh = bn_apply(c, gg), hn = bn_hat(c, gg);
+        float sg[4] = {sigmoidf_(gh.x), sigmoidf_(gh.y), sigmoidf_(gh.z), sigmoidf_(gh.w)};
+        // ds = sig * dm[dst] ; dsig = de_out + s * dm[dst] ; dghat = dsig * env * sg (1 - sg)
+        float4 ds = make_float4(env * sg[0] * dmd.x, env * sg[1] * dmd.y, env * sg[2] * dmd.z, env * sg[3] * dmd.w);
+        store4<T>(ds_t + o, ds);
+        a = make_float4((dd.x + ss.x * dmd.x) * env * sg[0] * (1.f - sg[0]), (dd.y + ss.y * dmd.y) * env * sg[1] * (1.f - sg[1]),
+                        (dd.z + ss.z * dmd.z) * env * sg[2] * (1.f - sg[2]), (dd.w + ss.w * dmd.w) * env * sg[3] * (1.f - sg[3]));
+        *reinterpret_cast<float4*>(dghat + o) = a;
+        b = make_float4(a.x * hn.x, a.y * hn.y, a.z * hn.z, a.w * hn.w);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// forward edge pass: gate, residual, deterministic per-destination sum
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict__ s, const float* __restrict__ e,
+                           const float* __restrict__ dist, const int32_t* __restrict__ row_ptr, int num_nodes, int D,
+                           const float* mean, const float* var, const float* w, const float* bias, float eps,
+                           float radius, int use_env, float* __restrict__ e_out, T* __restrict__ e_out_t,
+                           float* __restrict__ m) {
+    const int tpr = D >> 2, npb = 256 / tpr;
+    const int node = blockIdx.x * npb + threadIdx.x / tpr;
+    const int col = (threadIdx.x % tpr) * 4;
+    if (node >= num_nodes) return;
+    const BnCoef c = bn_coef(mean, var, w, bias, eps, col);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k0 = row_ptr[node], k1 = row_ptr[node + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int64_t o = (int64_t)k * D + col;
+        const float4 gg = *reinterpret_cast<const float4*>(g + o);
+        const float4 ss = *reinterpret_cast<const float4*>(s + o);
+        const float4 ee = *reinterpret_cast<const float4*>(e + o);
+        const float env = use_env ? cosine_cutoff(dist[k], radius) : 1.0f;
+        const float4 gh = bn_apply(c, gg);
+        const float4 sig = make_float4(env * sigmoidf_(gh.x), env * sigmoidf_(gh.y), env * sigmoidf_(gh.z), env * sigmoidf_(gh.w));
+        const float4 eo = make_float4(ee.x + sig.x, ee.y + sig.y, ee.z + sig.z, ee.w + sig.w);
+        *reinterpret_cast<float4*>(e_out + o) = eo;
+        if (e_out_t) store4<T>(e_out_t + o, eo);
+        acc.x += sig.x * ss.x; acc.y += sig.y * ss.y; acc.z += sig.z * ss.z; acc.w += sig.w * ss.w;
+    }
+    *reinterpret_cast<float4*>(m + (int64_t)node * D + col) = acc;
+}
+
+template <typename T>
+__global__ void node_update_kernel(const float* __restrict__ m, const float* __restrict__ x, int64_t total4, int D,
+                                   const float* mean, const float* var, const float* w, const float* bias, float eps,
+                                   float* __restrict__ x_out, T* __restrict__ x_out_t) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int64_t o = i * 4;
+    const int col = (int)(o % D);
+    const BnCoef c = bn_coef(mean, var, w, bias, eps, col);
+    const float4 y = bn_apply(c, *reinterpret_cast<const float4*>(m + o));
+    const float4 xi = *reinterpret_cast<const float4*>(x + o);
+    const float4 r = make_float4(siluf_(y.x) + xi.x, siluf_(y.y) + xi.y, siluf_(y.z) + xi.z, siluf_(y.w) + xi.w);
+    *reinterpret_cast<float4*>(x_out + o) = r;
+    if (x_out_t) store4<T>(x_out_t + o, r);
+}
+
+__global__ void node_bwd_apply_kernel(const float* __restrict__ dx, const float* __restrict__ m, int64_t total4, int D,
+                                      int num_nodes, const float* mean, const float* var, const float* w,
+                                      const float* bias, float eps, const float* __restrict__ sums, int training,
+                                      float* __restrict__ dm) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int64_t o = i * 4;
+    const int col = (int)(o % D);
+    const BnCoef c = bn_coef(mean, var, w, bias, eps, col);
+    const float4 mm = *reinterpret_cast<const float4*>(m + o);
+    const float4 g = *reinterpret_cast<const float4*>(dx + o);
+    const float4 y = bn_apply(c, mm), h = bn_hat(c, mm);
+    float dy[4] = {g.x * dsiluf_(y.x), g.y * dsiluf_(y.y), g.z * dsiluf_(y.z), g.w * dsiluf_(y.w)};
+    const float hh[4] = {h.x, h.y, h.z, h.w};
+    const float sc[4] = {c.scale.x, c.scale.y, c.scale.z, c.scale.w};
+    float out[4];
+    const float inv_n = 1.0f / (float)num_nodes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float corr = training ? (sums[col + j] * inv_n + hh[j] * sums[D + col + j] * inv_n) : 0.f;
+        out[j] = sc[j] * (dy[j] - corr);
+    }
+    *reinterpret_cast<float4*>(dm + o) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+template <typename T>
+__global__ void edge_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ dghat, int64_t total4,
+                                      int D, int64_t num_edges, const float* mean, const float* var, const float* w,
+                                      float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int64_t o = i * 4;
+    const int col = (int)(o % D);
+    const BnCoef c = bn_coef(mean, var, w, nullptr, eps, col);
+    const float4 h = bn_hat(c, *reinterpret_cast<const float4*>(g + o));
+    const float4 d = *reinterpret_cast<const float4*>(dghat + o);
+    const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    const float sc[4] = {c.scale.x, c.scale.y, c.scale.z, c.scale.w};
+    const float inv_n = 1.0f / (float)num_edges;
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float corr = training ? (sums[col + j] * inv_n + hh[j] * sums[D + col + j] * inv_n) : 0.f;
+        out[j] = sc[j] * (dd[j] - corr);
+    }
+    store4<T>(dg_t + o, make_float4(out[0], out[1], out[2], out[3]));
+}
+
+// out[n, :] = sum_{k in CSR row n} x[perm ? perm[k] : k, :]
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+segment_sum_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ ptr, const int32_t* __restrict__ perm,
+                   int num_nodes, int C, TO* __restrict__ out, int64_t ldo) {
+    const int tpr = C >> 2, npb = 256 / tpr;
+    const int node = blockIdx.x * npb + threadIdx.x / tpr;
+    const int col = (threadIdx.x % tpr) * 4;
+    if (node >= num_nodes) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k0 = ptr[node], k1 = ptr[node + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int64_t r = perm ? (int64_t)perm[k] : (int64_t)k;
+        const float4 v = load4<T>(x + r * ldx + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    store4<TO>(out + (int64_t)node * ldo + col, acc);
+}
+
+template <typename T>
+__global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, const T* __restrict__ z, int64_t ldz,
+                                 T* __restrict__ y, int64_t ldy, int64_t rows, int C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c4 = C >> 2;
+    if (i >= rows * c4) return;
+    const int64_t r = i / c4;
+    const int col = (int)(i % c4) * 4;
+    const float4 d = *reinterpret_cast<const float4*>(dy + r * ld_dy + col);
+    const float4 zz = load4<T>(z + r * ldz + col);
+    store4<T>(y + r * ldy + col, make_float4(d.x * dsiluf_(zz.x), d.y * dsiluf_(zz.y), d.z * dsiluf_(zz.z), d.w * dsiluf_(zz.w)));
+}
+
+template <typename T>
+__global__ void cast_rows_kernel(const float* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd,
+                                 int64_t rows, int C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c4 = C >> 2;
+    if (i >= rows * c4) return;
+    const int64_t r = i / c4;
+    const int col = (int)(i % c4) * 4;
+    store4<T>(dst + r * ldd + col, *reinterpret_cast<const float4*>(src + r * lds + col));
+}
+
+// feat[e, :] = [ cut(d) exp(-beta_k (exp(-alpha d) - mu_k)^2) (k < R) ; cart_dir (3, unless invariant) ; 0 ... ]
+template <typename T>
+__global__ void edge_features_kernel(const float* __restrict__ cart_dist, const float* __restrict__ cart_dir,
+                                     const float* __restrict__ means, const float* __restrict__ betas, int R,
+                                     float upper, int invariant, int64_t E, T* __restrict__ feat, int ld) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c4 = ld >> 2;
+    if (i >= E * c4) return;
+    const int64_t e = i / c4;
+    const int col = (int)(i % c4) * 4;
+    const float d = cart_dist[e];
+    const float alpha = 5.0f / upper;                 // models/utils.py:26 (cutoff_lower = 0)
+    const float ex = expf(alpha * (-d));              // models/utils.py:60
+    const float cut = cosine_cutoff(d, upper);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = col + j;
+        if (k < R) {
+            const float t = ex - means[k];
+            v[j] = cut * expf(-betas[k] * (t * t));
+        } else if (!invariant && k < R + 3) {
+            v[j] = cart_dir[e * 3 + (k - R)];
+        } else {
+            v[j] = 0.f;
+        }
+    }
+    store4<T>(feat + e * ld + col, make_float4(v[0], v[1], v[2], v[3]));
+}
+
+static inline bool row_shape_ok(int D) {
+    int tpr = D / 4;
+    return D % 4 == 0 && tpr >= 1 && tpr <= 256 && (256 % tpr) == 0;
+}
+
+}  // namespace cartnet
+
+using namespace cartnet;
+
+extern "C" {
+
+int64_t cartnet_colstats_workspace(int32_t C) { return (int64_t)kRedBlocksMax * 2 * C * (int64_t)sizeof(double); }
+
+int cartnet_colstats(const float* x, int64_t rows, int32_t C, int64_t ld, float* mean, float* var, float* running_mean,
+                     float* running_var, float momentum, double* partial, cartnet_stream_t stream) {
+    CN_CHECK_ARG(x && mean && var && partial && rows > 0, "colstats: bad arguments");
+    CN_CHECK_ARG(colreduce_shape_ok(C) && ld % 4 == 0, "colstats: C/4 must be a power of two <= 256 (C=%d)", C);
+    CN_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "colstats: running stats must come in pairs");
+    StatsF f{x, ld};
+    return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0,
+                         (cudaStream_t)stream);
+}
+
+int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld, float* out,
+                   double* partial, cartnet_stream_t stream) {
+    CN_CHECK_ARG(x && out && partial && rows >= 0, "colsum: bad arguments");
+    CN_CHECK_ARG(colreduce_shape_ok(C) && ld % 4 == 0, "colsum: C/4 must be a power of two <= 256 (C=%d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_is_t && prec == CARTNET_PREC_BF16) {
+        SumF<__nv_bfloat16> f{(const __nv_bfloat16*)x, ld};
+        return run_colreduce(f, rows, C, partial, FIN_SUMS, out, nullptr, nullptr, nullptr, 0.f, C, st);
+    }
+    SumF<float> f{(const float*)x, ld};
+    return run_colreduce(f, rows, C, partial, FIN_SUMS, out, nullptr, nullptr, nullptr, 0.f, C, st);
+}
+
+int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const float* means, const float* betas,
+                          int32_t num_rbf, float cutoff_upper, int32_t invariant, int64_t num_edges, void* feat,
+                          int32_t ld, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(cart_dist && means && betas && feat, "edge_features: null pointer");
+    CN_CHECK_ARG(invariant || cart_dir, "edge_features: cart_dir required unless invariant");
+    CN_CHECK_ARG(ld % 4 == 0 && ld >= num_rbf + (invariant ? 0 : 3), "edge_features: ld=%d too small", ld);
+    if (num_edges <= 0) return 0;
+    const int64_t total = num_edges * (ld / 4);
+    CN_DISPATCH_PREC(prec, {
+        edge_features_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            cart_dist, cart_dir, means, betas, num_rbf, cutoff_upper, invariant, num_edges, (T*)feat, ld);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_edge_gate_aggregate(const float* g, const float* s, const float* e, const float* dist,
+                                const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
+                                const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
+                                float eps, float radius, int32_t use_envelope, float* e_out, void* e_out_t, int32_t prec,
+                                float* m, cartnet_stream_t stream) {
+    CN_CHECK_ARG(row_ptr && bn_mean && bn_var && m, "edge_gate_aggregate: null pointer");
+    CN_CHECK_ARG(num_edges == 0 || (g && s && e && dist && e_out), "edge_gate_aggregate: null edge tensor");
+    CN_CHECK_ARG(row_shape_ok(D), "edge_gate_aggregate: unsupported D=%d", D);
+    if (num_nodes <= 0) return 0;
+    const int npb = 256 / (D / 4);
+    CN_DISPATCH_PREC(prec, {
+        edge_gate_aggregate_kernel<T><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
+            g, s, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope, e_out,
+            (T*)e_out_t, m);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_node_update(const float* m, const float* x, int32_t num_nodes, int32_t D, const float* bn_mean,
+                        const float* bn_var, const float* bn_weight, const float* bn_bias, float eps, float* x_out,
+                        void* x_out_t, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(m && x && bn_mean && bn_var && x_out && D % 4 == 0, "node_update: bad arguments");
+    if (num_nodes <= 0) return 0;
+    const int64_t total4 = (int64_t)num_nodes * D / 4;
+    CN_DISPATCH_PREC(prec, {
+        node_update_kernel<T><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+            m, x, total4, D, bn_mean, bn_var, bn_weight, bn_bias, eps, x_out, (T*)x_out_t);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_node_update_bwd_reduce(const float* dx_out, const float* m, int32_t num_nodes, int32_t D,
+                                   const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                   const float* bn_bias, float eps, float* sums, double* partial,
+                                   cartnet_stream_t stream) {
+    CN_CHECK_ARG(dx_out && m && bn_mean && bn_var && sums && partial && num_nodes > 0, "node_update_bwd_reduce: bad arguments");
+    CN_CHECK_ARG(colreduce_shape_ok(D), "node_update_bwd_reduce: unsupported D=%d", D);
+    NodeBwdF f{dx_out, m, D, bn_mean, bn_var, bn_weight, bn_bias, eps};
+    return run_colreduce(f, (int64_t)num_nodes, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 2 * D,
+                         (cudaStream_t)stream);
+}
+
+int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t num_nodes, int32_t D,
+                                  const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                  const float* bn_bias, float eps, const float* sums, int32_t training, float* dm,
+                                  cartnet_stream_t stream) {
+    CN_CHECK_ARG(dx_out && m && bn_mean && bn_var && dm && D % 4 == 0, "node_update_bwd_apply: bad arguments");
+    CN_CHECK_ARG(!training || sums, "node_update_bwd_apply: sums required in training mode");
+    if (num_nodes <= 0) return 0;
+    const int64_t total4 = (int64_t)num_nodes * D / 4;
+    node_bwd_apply_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        dx_out, m, total4, D, num_nodes, bn_mean, bn_var, bn_weight, bn_bias, eps, sums, training, dm);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
+                                 const float* de_out, const float* dm, int64_t num_edges, int32_t D,
+                                 const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
+                                 float eps, float radius, int32_t use_envelope, void* ds_t, float* dghat, int32_t prec,
+                                 float* sums, double* partial, cartnet_stream_t stream) {
+    CN_CHECK_ARG(g && s && dist && dst32 && de_out && dm && bn_mean && bn_var && ds_t && dghat && sums && partial &&
+                     num_edges > 0, "edge_gate_bwd_reduce: bad arguments");
+    CN_CHECK_ARG(colreduce_shape_ok(D), "edge_gate_bwd_reduce: unsupported D=%d", D);
+    CN_DISPATCH_PREC(prec, {
+        EdgeBwdF<T> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+                      (T*)ds_t, dghat};
+        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 2 * D,
+                             (cudaStream_t)stream);
+    });
+    return 0;
+}
+
+int cartnet_edge_gate_bwd_apply(const float* g, const float* dghat, int64_t num_edges, int32_t D, const float* bn_mean,
+                                const float* bn_var, const float* bn_weight, float eps, const float* sums,
+                                int32_t training, void* dg_t, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(g && dghat && bn_mean && bn_var && dg_t && D % 4 == 0, "edge_gate_bwd_apply: bad arguments");
+    CN_CHECK_ARG(!training || sums, "edge_gate_bwd_apply: sums required in training mode");
+    if (num_edges <= 0) return 0;
+    const int64_t total4 = num_edges * D / 4;
+    CN_DISPATCH_PREC(prec, {
+        edge_bwd_apply_kernel<T><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+            g, dghat, total4, D, num_edges, bn_mean, bn_var, bn_weight, eps, sums, training, (T*)dg_t);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const int32_t* perm, int32_t num_nodes,
+                        int32_t C, void* out, int64_t ldo, int32_t out_is_t, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(ptr && out && (x || num_nodes == 0), "segment_sum: null pointer");
+    CN_CHECK_ARG(row_shape_ok(C) && ldx % 4 == 0 && ldo % 4 == 0, "segment_sum: unsupported C=%d", C);
+    if (num_nodes <= 0) return 0;
+    const int npb = 256 / (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    CN_DISPATCH_PREC(prec, {
+        if (out_is_t)
+            segment_sum_kernel<T, T><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, ptr, perm, num_nodes, C, (T*)out, ldo);
+        else
+            segment_sum_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, ptr, perm, num_nodes, C, (float*)out, ldo);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy, int64_t rows,
+                      int32_t C, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(dy && z && y && C % 4 == 0 && ld_dy % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "dsilu_mul: bad arguments");
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (C / 4);
+    CN_DISPATCH_PREC(prec, {
+        dsilu_mul_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            dy, ld_dy, (const T*)z, ldz, (T*)y, ldy, rows, C);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C, int32_t prec,
+                      cartnet_stream_t stream) {
+    CN_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cast_rows: bad arguments");
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (C / 4);
+    CN_DISPATCH_PREC(prec, {
+        cast_rows_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (T*)dst, ldd, rows, C);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""autograd Functions that compose the C-ABI kernels into the two hot-path operators:
+
+  * edge_encoder -- the edge branch of Encoder.forward   (/root/reference/models/cartnet.py:133-138,156-159)
+  * cartnet_layer -- CartNet_layer.forward (message / aggregate / update)   (cartnet.py:204-274)
+
+Forward and backward are both hand-written (no autograd replay of eager ops). The first Linear of
+the gate / aggregate MLPs is split W1 = [W_i | W_j | W_e]: W_i x_i and W_j x_j are
+per-NODE projections (one small GEMM), gathered per edge inside the epilogue of the per-EDGE GEMM
+e @ W_e^T, which halves the edge FLOPs and removes the [E,768] concatenations. Mathematically
+identical to the reference; only the fp32 summation order differs (inside the 1e-5 budget).
+
+`prec` selects the GEMM operand type T: fp32 SIMT (1e-5 parity) or bf16 tcgen05 (2e-3 parity).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32, f32_storage, t_dtype
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _to_t(w: torch.Tensor, prec: int) -> torch.Tensor:
+    """weights are tiny (<= 1 MB): a torch cast is plumbing, not hot path"""
+    w = w.detach()
+    return w.contiguous() if f32_storage(prec) else w.to(torch.bfloat16).contiguous()
+
+
+class _EdgeEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, upper, invariant, prec, holder):
+        dim_edge = int(Wa.shape[1])
+        D2, D = int(Wa.shape[0]), int(Wb.shape[0])
+        KF = _round_up(dim_edge, {PREC_FP32: 4, PREC_BF16: 64, PREC_TF32: 32}[prec])   # tcgen05: whole 128-byte K blocks
+        T = t_dtype(prec)
+        dev = cart_dist.device
+        E = int(cart_dist.shape[0])
+        feat = ops.edge_features(cart_dist, cart_dir, means, betas, upper, invariant, KF, prec)
+        Wa_t = _to_t(F.pad(Wa.detach(), (0, KF - dim_edge)), prec)
+        Wb_t = _to_t(Wb, prec)
+        Z1 = torch.empty(E, D2, dtype=T, device=dev)
+        H1 = torch.empty(E, D2, dtype=T, device=dev)
+        ops.gemm(prec, feat, Wa_t, bias=ba.detach(), z_out=Z1, act=ACT_SILU, out_t=H1)
+        Z2 = torch.empty(E, D, dtype=T, device=dev)
+        e0 = torch.empty(E, D, dtype=torch.float32, device=dev)
+        e0_t = None if f32_storage(prec) else torch.empty(E, D, dtype=T, device=dev)
+        ops.gemm(prec, H1, Wb_t, bias=bb.detach(), z_out=Z2, act=ACT_SILU, out_f32=e0, out_t=e0_t)
+        holder["e_t"] = e0 if f32_storage(prec) else e0_t
+        ctx.save_for_backward(feat, Z1, H1, Z2, Wb)
+        ctx.prec, ctx.dim_edge = prec, dim_edge
+        return e0
+
+    @staticmethod
+    def backward(ctx, de0):
+        feat, Z1, H1, Z2, Wb = ctx.saved_tensors
+        prec = ctx.prec
+        T = t_dtype(prec)
+        dz2 = ops.dsilu_mul(de0.contiguous(), Z2, prec)                 # [E, D]
+        dWb = ops.gemm_tn(prec, dz2, H1)                                # [D, 2D]
+        dbb = ops.colsum(dz2, prec)
+        dz1 = torch.empty_like(Z1)
+        ops.gemm(prec, dz2, _to_t(Wb.t(), prec), act=ACT_MUL_DSILU, z_in=Z1, out_t=dz1)
+        dWa = ops.gemm_tn(prec, dz1, feat)[:, :ctx.dim_edge]            # [2D, dim_edge]
+        dba = ops.colsum(dz1, prec)
+        return None, None, None, None, dWa, dba, dWb, dbb, None, None, None, None
+
+
+def edge_encoder(cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, upper, invariant, prec):
+    """Returns (edge_attr fp32 [E,D], T-typed operand copy for the first layer)."""
+    holder = {}
+    e0 = _EdgeEncoderFn.apply(cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, float(upper), bool(invariant),
+                              prec, holder)
+    return e0, holder["e_t"]
+
+
+class _LayerFn(torch.autograd.Function):
+    """Inputs: x [N,D], e [E,D] (fp32) and the packed weights
+         W1n [4D,D] = [G1_i ; A1_i ; G1_j ; A1_j],  W1e [2D,D] = [G1_e ; A1_e],  b1 [2D] = [bg1 ; ba1],
+         G2, A2 [D,D], bg2, ba2 [D], BatchNorm affine (w1,b1n over edges; w2,b2n over nodes).
+       cfg: dict(plan, dist, x_t, e_t, prec, training, radius, use_envelope, momentum, bn buffers, holder)."""
+
+    @staticmethod
+    def forward(ctx, x, e, W1n, W1e, b1, G2, A2, bg2, ba2, w1, b1n, w2, b2n, cfg):
+        prec, plan, dist = cfg["prec"], cfg["plan"], cfg["dist"]
+        training = cfg["training"]
+        T = t_dtype(prec)
+        dev = x.device
+        N, D = int(x.shape[0]), int(x.shape[1])
+        E = int(e.shape[0])
+        x = x.detach().contiguous()
+        e = e.detach().contiguous()
+        x_t = cfg.get("x_t")
+        e_t = cfg.get("e_t")
+        if x_t is None:
+            x_t = ops.cast(x, prec)
+        if e_t is None:
+            e_t = ops.cast(e, prec)
+        W1n_t, W1e_t, G2_t, A2_t = (_to_t(w, prec) for w in (W1n, W1e, G2, A2))
+
+        # per-node projections P = x W1n^T : [:, 0:2D] dst-role (gate|aggr), [:, 2D:4D] src-role
+        P = torch.empty(N, 4 * D, dtype=T, device=dev)
+        ops.gemm(prec, x_t, W1n_t, out_t=P)
+        # per-edge first Linear with gathered projections, SiLU                       (cartnet.py:237,256)
+        Z = torch.empty(E, 2 * D, dtype=T, device=dev)
+        H = torch.empty(E, 2 * D, dtype=T, device=dev)
+        ops.gemm(prec, e_t, W1e_t, bias=b1.detach(), gather0=P[:, :2 * D], gidx0=plan.dst32,
+                 gather1=P[:, 2 * D:], gidx1=plan.src32, z_out=Z, act=ACT_SILU, out_t=H)
+        # second Linears                                                              (cartnet.py:190,195)
+        g = torch.empty(E, D, dtype=torch.float32, device=dev)
+        s = torch.empty(E, D, dtype=torch.float32, device=dev)
+        ops.gemm(prec, H[:, :D], G2_t, bias=bg2.detach(), out_f32=g)
+        ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_f32=s)
+        # edge BatchNorm statistics (global barrier over E rows)                      (cartnet.py:238)
+        if training:
+            mean1, var1 = ops.colstats(g, cfg["rm1"], cfg["rv1"], cfg["momentum1"])
+        else:
+            mean1, var1 = cfg["rm1"], cfg["rv1"]
+        e_out, e_out_t, m = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
+                                                    b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True)
+        if training:
+            mean2, var2 = ops.colstats(m, cfg["rm2"], cfg["rv2"], cfg["momentum2"])
+        else:
+            mean2, var2 = cfg["rm2"], cfg["rv2"]
+        x_out, x_out_t = ops.node_update(m, x, mean2, var2, w2.detach(), b2n.detach(), prec, True)   # cartnet.py:269,223
+        cfg["holder"]["x_t"], cfg["holder"]["e_t"] = x_out_t, e_out_t
+
+        ctx.save_for_backward(x_t, e_t, Z, H, g, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
+        ctx.cfg = dict(prec=prec, plan=plan, dist=dist, training=training, radius=cfg["radius"],
+                       use_envelope=cfg["use_envelope"])
+        return x_out, e_out
+
+    @staticmethod
+    def backward(ctx, dx_out, de_out):
+        (x_t, e_t, Z, H, g, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n) = ctx.saved_tensors
+        c = ctx.cfg
+        prec, plan, training = c["prec"], c["plan"], c["training"]
+        T = t_dtype(prec)
+        dev = g.device
+        N, D = int(m.shape[0]), int(m.shape[1])
+        E = int(g.shape[0])
+        if dx_out is None:
+            dx_out = torch.zeros(N, D, dtype=torch.float32, device=dev)
+        if de_out is None:
+            de_out = torch.zeros(E, D, dtype=torch.float32, device=dev)
+        dx_out = dx_out.contiguous()
+        de_out = de_out.contiguous()
+
+        # node side: x' = silu(BN2(m)) + x
+        dm, sums2 = ops.node_update_bwd(dx_out, m, mean2, var2, w2, b2n, training)
+        # edge side: sig = env * sigmoid(BN1(g)); e' = e + sig; m = segsum(sig * s)
+        ds_t, dg_t, sums1 = ops.edge_gate_bwd(g, s, c["dist"], plan.dst32, de_out, dm, mean1, var1, w1, b1n,
+                                              c["radius"], c["use_envelope"], training, prec)
+        # second Linears: dgrad (+ SiLU') and wgrad
+        dZ = torch.empty(E, 2 * D, dtype=T, device=dev)
+        ops.gemm(prec, dg_t, _to_t(G2.t(), prec), act=ACT_MUL_DSILU, z_in=Z[:, :D], out_t=dZ[:, :D])
+        ops.gemm(prec, ds_t, _to_t(A2.t(), prec), act=ACT_MUL_DSILU, z_in=Z[:, D:], out_t=dZ[:, D:])
+        dG2 = ops.gemm_tn(prec, dg_t, H[:, :D])
+        dA2 = ops.gemm_tn(prec, ds_t, H[:, D:])
+        dbg2 = ops.colsum(dg_t, prec)
+        dba2 = ops.colsum(ds_t, prec)
+        # first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
+        de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
+        ops.gemm(prec, dZ, _to_t(W1e.t(), prec), resid=de_out, out_f32=de_in)
+        dW1e = ops.gemm_tn(prec, dZ, e_t)
+        db1 = ops.colsum(dZ, prec)
+        # first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
+        dP = torch.empty(N, 4 * D, dtype=T, device=dev)
+        ops.segment_sum(dZ, plan.row_ptr, None, N, dP[:, :2 * D], prec)
+        ops.segment_sum(dZ, plan.col_ptr, plan.perm_src, N, dP[:, 2 * D:], prec)
+        dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
+        ops.gemm(prec, dP, _to_t(W1n.t(), prec), resid=dx_out, out_f32=dx_in)
+        dW1n = ops.gemm_tn(prec, dP, x_t)
+        dw1, db1n = sums1[D:].clone(), sums1[:D].clone()
+        dw2, db2n = sums2[D:].clone(), sums2[:D].clone()
+        return dx_in, de_in, dW1n, dW1e, db1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n, None
+
+
+def cartnet_layer(x, e, packed, cfg):
+    """packed = (W1n, W1e, b1, G2, A2, bg2, ba2, w1, b1n, w2, b2n). Returns x_out, e_out and fills
+    cfg['holder'] with the T-typed operand copies for the next layer."""
+    return _LayerFn.apply(x, e, *packed, cfg)

@@ -1,0 +1,373 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point group).
+
+Each wrapper checks devices/dtypes/strides, allocates outputs with torch (the library never
+allocates), passes raw device pointers plus the current CUDA stream, and raises on a non-zero
+return code. There is no CPU path here: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32  # noqa: F401
+
+EPS_BN = 1e-5
+
+
+def t_dtype(prec: int) -> torch.dtype:
+    """storage type of the GEMM operands: bf16 for PREC_BF16, fp32 for PREC_FP32 (SIMT) and PREC_TF32 (tcgen05)"""
+    return torch.bfloat16 if prec == PREC_BF16 else torch.float32
+
+
+def f32_storage(prec: int) -> bool:
+    return prec != PREC_BF16
+
+
+def launch_count() -> int:
+    return int(_lib.load().cartnet_launch_count())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str, rowmajor: bool = True):
+    if not t.is_cuda:
+        raise RuntimeError("cartnet_b200: %s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != dtype:
+        raise TypeError("cartnet_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if rowmajor and t.dim() >= 1 and t.numel() > 0 and t.stride(-1) != 1:
+        raise ValueError("cartnet_b200: %s must have unit stride in its last dimension" % name)
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    """leading dimension (elements) of a 2-D row-major view"""
+    return t.stride(0) if t.dim() == 2 and t.shape[0] > 1 else (t.shape[-1] if t.dim() == 2 else 0)
+
+
+def _ld2(t: torch.Tensor) -> int:
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.shape[0] > 1:
+        return int(t.stride(0))
+    return int(max(t.shape[1], t.stride(0)))
+
+
+_scratch = {}
+
+
+def _partial(device, nbytes: int) -> torch.Tensor:
+    """fp64 scratch for the fixed-order column reductions (stream-ordered reuse)."""
+    key = (device, "partial")
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device, "ws")
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = torch.empty((nbytes + 3) // 4 + 64, dtype=torch.float32, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------- graph build
+def nlist_build(pos, cell, natoms, radius: float, pbc_mask: int = 7, batch_max_reps: bool = True,
+                want_cart: bool = True, want_i32: bool = False):
+    """Periodic radius graph (dataset/utils.py:57-237). Returns dict with edge_index [2,E] i64,
+    unit_cell, dist, direction (+ cart_dist, cart_dir, src32, dst32, row_ptr when requested)."""
+    lib = _lib.load()
+    pos = _req(pos.contiguous(), torch.float32, "pos")
+    cell = _req(cell.reshape(-1, 3, 3).contiguous(), torch.float32, "cell")
+    dev = pos.device
+    natoms = natoms.to(device=dev, dtype=torch.int64).reshape(-1)
+    B, N = int(natoms.numel()), int(pos.shape[0])
+    crystal_ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    crystal_ptr[1:] = torch.cumsum(natoms, 0).to(torch.int32)
+    node_crystal = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), natoms, output_size=N)
+    reps = torch.empty(B, 3, dtype=torch.int32, device=dev)
+    reps_max = torch.zeros(3, dtype=torch.int32, device=dev)
+    st = _stream()
+    _lib.check(lib.cartnet_nlist_reps(_p(cell), B, float(radius), int(pbc_mask), _p(reps), _p(reps_max), st), "nlist_reps")
+    reps_arg, stride = (reps_max, 0) if batch_max_reps else (reps, 3)
+    r2 = C.c_float(float(radius) * float(radius)).value      # double product rounded to fp32 (utils.py:202)
+    row_count = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.check(lib.cartnet_nlist_count(_p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2,
+                                       _p(reps_arg), stride, _p(row_count), st), "nlist_count")
+    row_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    _lib.check(lib.cartnet_exclusive_scan_i32(_p(row_count), N, _p(row_ptr), st), "exclusive_scan")
+    E = int(row_ptr[-1].item()) if N > 0 else 0          # the one host sync: output sizes
+    out = {
+        "edge_index": torch.empty(2, E, dtype=torch.int64, device=dev),
+        "unit_cell": torch.empty(E, 3, dtype=torch.float32, device=dev),
+        "dist": torch.empty(E, dtype=torch.float32, device=dev),
+        "direction": torch.empty(E, 3, dtype=torch.float32, device=dev),
+        "row_ptr": row_ptr, "reps": reps, "reps_max": reps_max,
+    }
+    if want_cart:
+        out["cart_dist"] = torch.empty(E, dtype=torch.float32, device=dev)
+        out["cart_dir"] = torch.empty(E, 3, dtype=torch.float32, device=dev)
+    if want_i32:
+        out["src32"] = torch.empty(E, dtype=torch.int32, device=dev)
+        out["dst32"] = torch.empty(E, dtype=torch.int32, device=dev)
+    _lib.check(lib.cartnet_nlist_fill(
+        _p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2, _p(reps_arg), stride, _p(row_ptr),
+        _p(out["edge_index"]), E, _p(out["unit_cell"]), _p(out["dist"]), _p(out["direction"]),
+        _p(out.get("cart_dist")), _p(out.get("cart_dir")), _p(out.get("src32")), _p(out.get("dst32")), st), "nlist_fill")
+    return out
+
+
+@dataclass
+class GraphPlan:
+    """int32 indexing for the layer kernels; built once per batch and reused by all layers."""
+    num_nodes: int
+    num_edges: int
+    src32: torch.Tensor
+    dst32: torch.Tensor
+    row_ptr: torch.Tensor            # dst CSR (edges are dst-sorted)
+    col_ptr: torch.Tensor            # src CSR
+    perm_src: torch.Tensor           # edge ids grouped by src
+    perm_dst: Optional[torch.Tensor] = None   # only when the caller's edges were NOT dst-sorted
+    key: tuple = ()
+
+
+def graph_plan(edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
+    lib = _lib.load()
+    edge_index = _req(edge_index.contiguous(), torch.int64, "edge_index")
+    dev = edge_index.device
+    E = int(edge_index.shape[1])
+    st = _stream()
+    src32 = torch.empty(E, dtype=torch.int32, device=dev)
+    dst32 = torch.empty(E, dtype=torch.int32, device=dev)
+    flags = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(lib.cartnet_graph_split(_p(edge_index), E, num_nodes, _p(src32), _p(dst32), _p(flags), st), "graph_split")
+    unsorted, oob = (int(v) for v in flags.tolist())        # host sync, once per batch
+    if oob:
+        raise IndexError("cartnet_b200: edge_index has entries outside [0, %d)" % num_nodes)
+    cursor = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)
+
+    def csr(keys):
+        ptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        _lib.check(lib.cartnet_graph_csr(_p(keys), E, num_nodes, _p(ptr), _p(perm), _p(cursor), st), "graph_csr")
+        return ptr, perm
+
+    perm_dst = None
+    row_ptr, perm_d = csr(dst32)
+    if unsorted:   # bring the edges into dst-sorted order; callers permute their edge tensors with perm_dst
+        perm_dst = perm_d.to(torch.int64)
+        src32 = src32[perm_dst].contiguous()
+        dst32 = dst32[perm_dst].contiguous()
+    col_ptr, perm_src = csr(src32)
+    return GraphPlan(num_nodes, E, src32, dst32, row_ptr, col_ptr, perm_src, perm_dst)
+
+
+# ----------------------------------------------------------------------------- featuriser
+def edge_features(cart_dist, cart_dir, means, betas, cutoff_upper: float, invariant: bool, ld: int, prec: int):
+    lib = _lib.load()
+    cart_dist = _req(cart_dist.contiguous(), torch.float32, "cart_dist")
+    if cart_dist.dim() != 1:
+        raise ValueError("cart_dist must be 1-D [E] (cartnet.py:241 unsqueezes it)")
+    E = int(cart_dist.shape[0])
+    if not invariant:
+        cart_dir = _req(cart_dir.contiguous(), torch.float32, "cart_dir")
+    feat = torch.empty(E, ld, dtype=t_dtype(prec), device=cart_dist.device)
+    _lib.check(lib.cartnet_edge_features(_p(cart_dist), None if invariant else _p(cart_dir), _p(means), _p(betas),
+                                         int(means.numel()), float(cutoff_upper), int(bool(invariant)), E, _p(feat),
+                                         ld, prec, _stream()), "edge_features")
+    return feat
+
+
+# ----------------------------------------------------------------------------- GEMMs
+def gemm(prec: int, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1=None,
+         z_out=None, act: int = ACT_NONE, z_in=None, resid=None, out_f32=None, out_t=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T with the fused epilogue of `cartnet_gemm_t`. Outputs are the
+    caller-provided (possibly strided) views z_out / out_f32 / out_t."""
+    lib = _lib.load()
+    T = t_dtype(prec)
+    _req(A, T, "A"); _req(B, T, "B")
+    M, K = int(A.shape[0]), int(A.shape[1])
+    N = int(B.shape[0])
+    if int(B.shape[1]) != K:
+        raise ValueError("gemm: K mismatch %d vs %d" % (K, int(B.shape[1])))
+    d = _lib.GemmDesc()
+    d.prec, d.M, d.N, d.K = prec, M, N, K
+    d.A, d.lda, d.B, d.ldb = _p(A), _ld2(A), _p(B), _ld2(B)
+    d.bias = _p(_req(bias, torch.float32, "bias")) if bias is not None else None
+    if gather0 is not None:
+        _req(gather0, T, "gather0"); _req(gidx0, torch.int32, "gidx0")
+        d.gather0, d.gidx0, d.ldg = _p(gather0), _p(gidx0), _ld2(gather0)
+    if gather1 is not None:
+        _req(gather1, T, "gather1"); _req(gidx1, torch.int32, "gidx1")
+        if gather0 is not None and _ld2(gather1) != d.ldg:
+            raise ValueError("gemm: gather0/gather1 must share a leading dimension")
+        d.gather1, d.gidx1, d.ldg = _p(gather1), _p(gidx1), _ld2(gather1)
+    if z_out is not None:
+        _req(z_out, T, "z_out"); d.z_out, d.ldz = _p(z_out), _ld2(z_out)
+    d.act = act
+    if z_in is not None:
+        _req(z_in, T, "z_in"); d.z_in, d.ldzin = _p(z_in), _ld2(z_in)
+    if resid is not None:
+        _req(resid, torch.float32, "resid"); d.resid, d.ldr = _p(resid), _ld2(resid)
+    if out_f32 is not None:
+        _req(out_f32, torch.float32, "out_f32"); d.out_f32, d.ldo = _p(out_f32), _ld2(out_f32)
+    if out_t is not None:
+        _req(out_t, T, "out_t"); d.out_t, d.ldt = _p(out_t), _ld2(out_t)
+    for nm, t in (("z_out", z_out), ("z_in", z_in), ("resid", resid), ("out_f32", out_f32), ("out_t", out_t)):
+        if t is not None and (int(t.shape[0]) != M or int(t.shape[1]) != N):
+            raise ValueError("gemm: %s has shape %s, expected [%d,%d]" % (nm, tuple(t.shape), M, N))
+    _lib.check(lib.cartnet_gemm(C.byref(d), _stream()), "gemm")
+
+
+def gemm_tn(prec: int, A, B) -> torch.Tensor:
+    """C[M,N] fp32 = A[K,M]^T @ B[K,N] (deterministic split-K)."""
+    lib = _lib.load()
+    T = t_dtype(prec)
+    _req(A, T, "A"); _req(B, T, "B")
+    K, M, N = int(A.shape[0]), int(A.shape[1]), int(B.shape[1])
+    if int(B.shape[0]) != K:
+        raise ValueError("gemm_tn: K mismatch")
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    nbytes = int(lib.cartnet_gemm_tn_workspace(prec, M, N, K))
+    ws = _workspace(A.device, nbytes)
+    _lib.check(lib.cartnet_gemm_tn(prec, M, N, K, _p(A), _ld2(A), _p(B), _ld2(B), _p(out), N, _p(ws),
+                                   ws.numel() * 4, _stream()), "gemm_tn")
+    return out
+
+
+# ----------------------------------------------------------------------------- reductions
+def colstats(x, running_mean=None, running_var=None, momentum: float = 0.1):
+    """Per-column mean / biased variance over rows; updates running stats in place (train-mode BN)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    rows, Cc = int(x.shape[0]), int(x.shape[1])
+    mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    var = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    part = _partial(x.device, int(lib.cartnet_colstats_workspace(Cc)))
+    _lib.check(lib.cartnet_colstats(_p(x), rows, Cc, _ld2(x), _p(mean), _p(var), _p(running_mean), _p(running_var),
+                                    float(momentum), _p(part), _stream()), "colstats")
+    return mean, var
+
+
+def colsum(x, prec: int) -> torch.Tensor:
+    lib = _lib.load()
+    is_t = 0 if x.dtype == torch.float32 else 1
+    _req(x, torch.float32 if not is_t else t_dtype(prec), "x")
+    rows, Cc = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    part = _partial(x.device, int(lib.cartnet_colstats_workspace(Cc)))
+    _lib.check(lib.cartnet_colsum(_p(x), is_t, prec, rows, Cc, _ld2(x), _p(out), _p(part), _stream()), "colsum")
+    return out
+
+
+# ----------------------------------------------------------------------------- layer passes
+def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes: int, bn_mean, bn_var, bn_w, bn_b, radius: float,
+                        use_envelope: bool, prec: int, want_shadow: bool):
+    lib = _lib.load()
+    for nm, t in (("g", g), ("s", s), ("e", e)):
+        _req(t, torch.float32, nm)
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % nm)
+    E, D = int(e.shape[0]), int(e.shape[1])
+    e_out = torch.empty_like(e)
+    e_out_t = torch.empty(E, D, dtype=t_dtype(prec), device=e.device) if (want_shadow and not f32_storage(prec)) else None
+    m = torch.empty(num_nodes, D, dtype=torch.float32, device=e.device)
+    _lib.check(lib.cartnet_edge_gate_aggregate(
+        _p(g), _p(s), _p(e), _p(dist), _p(row_ptr), num_nodes, E, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b),
+        EPS_BN, float(radius), int(bool(use_envelope)), _p(e_out), _p(e_out_t), prec, _p(m), _stream()),
+        "edge_gate_aggregate")
+    return e_out, (e_out_t if e_out_t is not None else (e_out if f32_storage(prec) else None)), m
+
+
+def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec: int, want_shadow: bool):
+    lib = _lib.load()
+    _req(m, torch.float32, "m"); _req(x, torch.float32, "x")
+    x = x.contiguous()
+    N, D = int(x.shape[0]), int(x.shape[1])
+    x_out = torch.empty_like(x)
+    x_out_t = torch.empty(N, D, dtype=t_dtype(prec), device=x.device) if (want_shadow and not f32_storage(prec)) else None
+    _lib.check(lib.cartnet_node_update(_p(m), _p(x), N, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b), EPS_BN,
+                                       _p(x_out), _p(x_out_t), prec, _stream()), "node_update")
+    return x_out, (x_out_t if x_out_t is not None else (x_out if f32_storage(prec) else None))
+
+
+def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training: bool):
+    """Returns dm [N,D] and sums [2D] (sum dy | sum dy*yhat) = (d bias | d weight) of norm2."""
+    lib = _lib.load()
+    dx_out = _req(dx_out.contiguous(), torch.float32, "dx_out")
+    N, D = int(m.shape[0]), int(m.shape[1])
+    sums = torch.empty(2 * D, dtype=torch.float32, device=m.device)
+    part = _partial(m.device, int(lib.cartnet_colstats_workspace(D)))
+    st = _stream()
+    _lib.check(lib.cartnet_node_update_bwd_reduce(_p(dx_out), _p(m), N, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b),
+                                                  EPS_BN, _p(sums), _p(part), st), "node_update_bwd_reduce")
+    dm = torch.empty_like(m)
+    _lib.check(lib.cartnet_node_update_bwd_apply(_p(dx_out), _p(m), N, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b),
+                                                 EPS_BN, _p(sums), int(bool(training)), _p(dm), st), "node_update_bwd_apply")
+    return dm, sums
+
+
+def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, radius: float, use_envelope: bool,
+                  training: bool, prec: int):
+    """Returns ds_t, dg_t (T, [E,D]) and sums [2D] (d bias | d weight of the edge BatchNorm)."""
+    lib = _lib.load()
+    de_out = _req(de_out.contiguous(), torch.float32, "de_out")
+    E, D = int(g.shape[0]), int(g.shape[1])
+    T = t_dtype(prec)
+    ds_t = torch.empty(E, D, dtype=T, device=g.device)
+    dg_t = torch.empty(E, D, dtype=T, device=g.device)
+    dghat = torch.empty(E, D, dtype=torch.float32, device=g.device)
+    sums = torch.empty(2 * D, dtype=torch.float32, device=g.device)
+    part = _partial(g.device, int(lib.cartnet_colstats_workspace(D)))
+    st = _stream()
+    _lib.check(lib.cartnet_edge_gate_bwd_reduce(
+        _p(g), _p(s), _p(dist), _p(dst32), _p(de_out), _p(dm), E, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b), EPS_BN,
+        float(radius), int(bool(use_envelope)), _p(ds_t), _p(dghat), prec, _p(sums), _p(part), st), "edge_gate_bwd_reduce")
+    _lib.check(lib.cartnet_edge_gate_bwd_apply(_p(g), _p(dghat), E, D, _p(bn_mean), _p(bn_var), _p(bn_w), EPS_BN,
+                                               _p(sums), int(bool(training)), _p(dg_t), prec, st), "edge_gate_bwd_apply")
+    return ds_t, dg_t, sums
+
+
+def segment_sum(x, ptr, perm, num_nodes: int, out, prec: int):
+    """out[n,:] = sum over CSR row n of x[perm[k],:]; `out` is a caller-provided [N,C] view (T or fp32)."""
+    lib = _lib.load()
+    _req(x, t_dtype(prec), "x")
+    Cc = int(x.shape[1])
+    out_is_t = 0 if (out.dtype == torch.float32 and not f32_storage(prec)) else 1
+    _lib.check(lib.cartnet_segment_sum(_p(x), _ld2(x), _p(ptr), _p(perm), num_nodes, Cc, _p(out), _ld2(out),
+                                       out_is_t, prec, _stream()), "segment_sum")
+    return out
+
+
+def dsilu_mul(dy, z, prec: int) -> torch.Tensor:
+    lib = _lib.load()
+    _req(dy, torch.float32, "dy"); _req(z, t_dtype(prec), "z")
+    rows, Cc = int(z.shape[0]), int(z.shape[1])
+    y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=z.device)
+    _lib.check(lib.cartnet_dsilu_mul(_p(dy), _ld2(dy), _p(z), _ld2(z), _p(y), Cc, rows, Cc, prec, _stream()), "dsilu_mul")
+    return y
+
+
+def cast(x, prec: int) -> torch.Tensor:
+    """fp32 -> T operand copy (identity object for the fp32 path)."""
+    if f32_storage(prec):
+        return x
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    rows, Cc = int(x.shape[0]), int(x.shape[1])
+    y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=x.device)
+    _lib.check(lib.cartnet_cast_rows(_p(x), _ld2(x), _p(y), Cc, rows, Cc, prec, _stream()), "cast_rows")
+    return y

@@ -1,0 +1,232 @@
+/* cartnet_b200 -- C ABI of the B200-native CartNet hot path (libcartnet_b200.so).
+ *
+ * Everything the Python host code (cartnet_b200/) calls on the device goes through the
+ * entry points below: plain pointers, sizes and PODs, no torch types, no C++ exceptions.
+ * All pointers are DEVICE pointers unless marked "host". Every tensor is allocated and
+ * owned by the caller; the library never allocates or frees device memory. Calls are
+ * stateless and stream-ordered on `stream` (a cudaStream_t), so one process per GPU is safe.
+ * Return value: 0 on success, non-zero on error; cartnet_last_error() (thread-local)
+ * describes the last failure.
+ *
+ * The reference (imatge-upc/CartNet) is pure Python and has no FFI; each group cites the
+ * reference lines (relative to /root/reference) whose eager-op chain it replaces.
+ *
+ * "T" below is the GEMM operand type selected by `prec`:
+ *   CARTNET_PREC_FP32 : T = float,         GEMMs on the fp32 SIMT pipe  (1e-5 parity path)
+ *   CARTNET_PREC_BF16 : T = __nv_bfloat16, GEMMs on tcgen05/TMEM fed by TMA (2e-3 path)
+ *   CARTNET_PREC_TF32 : T = float,         GEMMs on tcgen05 kind::tf32 reading the fp32 tensors directly
+ */
+#ifndef CARTNET_B200_H
+#define CARTNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cartnet_stream_t; /* cudaStream_t */
+
+enum { CARTNET_PREC_FP32 = 0, CARTNET_PREC_BF16 = 1, CARTNET_PREC_TF32 = 2 };
+enum { CARTNET_ACT_NONE = 0, CARTNET_ACT_SILU = 1, CARTNET_ACT_MUL_DSILU = 2 };
+
+int cartnet_version(void);
+const char* cartnet_last_error(void);
+/* 1 if the visible device is sm_100 (B200); the bf16 path needs it. */
+int cartnet_device_ok(int device);
+/* Number of kernels this library has launched in this process so far (bench.py's gpu_launches). */
+int64_t cartnet_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Periodic radius graph -- replaces dataset/utils.py:57-237 (radius_graph_pbc) and the
+ * callers' post-processing dataset/figshare_dataset.py:67-68.
+ * Edge set AND order are bit-exact: (dst, src, cell) lexicographic, 1e-4 < d^2 <= r^2,
+ * fp32 arithmetic without FMA contraction in the reference's operation order.
+ * ------------------------------------------------------------------------------------- */
+
+/* rep_k = ceil(radius * ||(a_i x a_j)/V||) per crystal (utils.py:135-156).
+ * reps_out[B,3] int32. If reps_max (int32[3], pre-zeroed) is non-null it receives the max over the
+ * batch (utils.py:163). pbc_mask bit k set = axis k periodic. */
+int cartnet_nlist_reps(const float* cell, int32_t num_crystals, float radius, int32_t pbc_mask,
+                       int32_t* reps_out, int32_t* reps_max, cartnet_stream_t stream);
+
+/* Pass 1: row_count[n] = number of edges whose destination is atom n.
+ * crystal_ptr[B+1]: first atom of each crystal; node_crystal[N]: crystal of each atom.
+ * reps[B,3] per crystal when reps_stride = 3, or one shared int32[3] (batch max) when reps_stride = 0.
+ * radius_sq = (float)(radius*radius) rounded from the double product like torch.le does (utils.py:202). */
+int cartnet_nlist_count(const float* pos, const float* cell, const int32_t* crystal_ptr,
+                        const int32_t* node_crystal, int32_t num_nodes, float radius, float radius_sq,
+                        const int32_t* reps, int32_t reps_stride, int32_t* row_count,
+                        cartnet_stream_t stream);
+
+/* out[0] = 0, out[i+1] = sum_{j<=i} in[j]  (n+1 outputs). Single-launch, deterministic. */
+int cartnet_exclusive_scan_i32(const int32_t* in, int32_t n, int32_t* out, cartnet_stream_t stream);
+
+/* Pass 2: writes the edges of row n at [row_ptr[n], row_ptr[n+1]).
+ * edge_index[2,E] int64 (row 0 = src j, row 1 = dst i; utils.py:235), unit_cell[E,3] f32,
+ * dist[E] = sqrt(d^2), direction[E,3] = pos[dst] - (pos[src] + offset)  (utils.py:193-198,237).
+ * Optional (may be null): cart_dist[E] = ||direction||, cart_dir[E,3] = direction/max(||.||,1e-12)
+ * (figshare_dataset.py:67-68); src32/dst32[E] int32 copies for the layer kernels. */
+int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* crystal_ptr,
+                       const int32_t* node_crystal, int32_t num_nodes, float radius, float radius_sq,
+                       const int32_t* reps, int32_t reps_stride, const int32_t* row_ptr,
+                       int64_t* edge_index, int64_t num_edges, float* unit_cell, float* dist,
+                       float* direction, float* cart_dist, float* cart_dir, int32_t* src32,
+                       int32_t* dst32, cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Graph plan for the layer kernels -- replaces PyG MessagePassing's lift/scatter indexing
+ * (call at models/cartnet.py:218-221) and torch_scatter.scatter (cartnet.py:259).
+ * ------------------------------------------------------------------------------------- */
+
+/* edge_index[2,E] int64 -> src32/dst32 int32; flags[0] = 1 if dst is non-decreasing, flags[1] = 1 if
+ * any index is outside [0, num_nodes). */
+int cartnet_graph_split(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes,
+                        int32_t* src32, int32_t* dst32, int32_t* flags, cartnet_stream_t stream);
+
+/* Counting-sort CSR of `keys[E]` (values in [0,num_nodes)): ptr[num_nodes+1], perm[E] = edge ids
+ * grouped by key, ascending edge id inside a group (deterministic). `cursor` is int32[num_nodes]
+ * scratch. When keys are already sorted perm is the identity. */
+int cartnet_graph_csr(const int32_t* keys, int64_t num_edges, int32_t num_nodes, int32_t* ptr,
+                      int32_t* perm, int32_t* cursor, cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Edge featuriser -- replaces models/utils.py:56-61,87-91 and the cat at cartnet.py:159.
+ * feat[E, ld] (T): cols 0..num_rbf-1 = cut(d)*exp(-beta_k (exp(-alpha d) - mu_k)^2), then (unless
+ * invariant) 3 cols cart_dir, remaining cols up to ld zero.
+ * ------------------------------------------------------------------------------------- */
+int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const float* means,
+                          const float* betas, int32_t num_rbf, float cutoff_upper, int32_t invariant,
+                          int64_t num_edges, void* feat, int32_t ld, int32_t prec,
+                          cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense contractions -- replace the addmm/mm chains of cartnet.py:133-136,187-196 and their
+ * autograd backward. The gathered epilogue implements the split of the first Linear
+ * W1 = [W_i | W_j | W_e]: per-node projections are added per edge.
+ * ------------------------------------------------------------------------------------- */
+typedef struct cartnet_gemm {
+    int32_t prec;            /* CARTNET_PREC_* */
+    int32_t M, N, K;         /* C[M,N] = A[M,K] * B[N,K]^T ; bf16: K % 64 == 0, N % 64 == 0 */
+    const void* A;           /* T, row-major, leading dimension lda (elements) */
+    int64_t lda;
+    const void* B;           /* T, [N,K] row-major (PyTorch Linear weight layout), ld = ldb */
+    int64_t ldb;
+    /* epilogue, applied in this order; null pointer = step skipped */
+    const float* bias;       /* v += bias[col] */
+    const void* gather0;     /* v += gather0[gidx0[row]*ldg + col]      (T) */
+    const int32_t* gidx0;
+    const void* gather1;     /* v += gather1[gidx1[row]*ldg + col]      (T) */
+    const int32_t* gidx1;
+    int64_t ldg;
+    void* z_out;             /* z_out[row*ldz + col] = v                (T) */
+    int64_t ldz;
+    int32_t act;             /* CARTNET_ACT_*: none | v = silu(v) | v *= silu'(z_in[row*ldzin+col]) */
+    int32_t _pad;
+    const void* z_in;        /* T */
+    int64_t ldzin;
+    const float* resid;      /* v += resid[row*ldr + col] */
+    int64_t ldr;
+    float* out_f32;          /* out_f32[row*ldo + col] = v */
+    int64_t ldo;
+    void* out_t;             /* out_t[row*ldt + col] = (T) v */
+    int64_t ldt;
+} cartnet_gemm_t;
+
+int cartnet_gemm(const cartnet_gemm_t* desc /* host */, cartnet_stream_t stream);
+
+/* C[M,N] (fp32, ldc) = sum_k A[k, 0:M]^T * B[k, 0:N]  -- the weight-gradient contraction over
+ * K = edges (or nodes). A: [K, lda] T, B: [K, ldb] T. Split-K with a fixed-order second pass, so the
+ * result is deterministic. workspace: fp32, at least cartnet_gemm_tn_workspace(...) bytes. */
+int64_t cartnet_gemm_tn_workspace(int32_t prec, int32_t M, int32_t N, int64_t K);
+int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A, int64_t lda,
+                    const void* B, int64_t ldb, float* C, int64_t ldc, float* workspace,
+                    int64_t workspace_bytes, cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Column statistics / BatchNorm pieces -- replace nn.BatchNorm1d over E rows (cartnet.py:198,238)
+ * and over N rows (cartnet.py:199,269). Sums are accumulated in fp64 in a fixed order.
+ * ------------------------------------------------------------------------------------- */
+
+/* mean[C], var[C] (biased) of x[rows, C] (fp32, ld). If running_mean/var non-null they are updated in
+ * place like nn.BatchNorm1d in train mode: r = (1-momentum) r + momentum * stat, with the UNBIASED
+ * variance. partial: fp64 scratch, >= cartnet_colstats_workspace(C) bytes. */
+int64_t cartnet_colstats_workspace(int32_t C);
+int cartnet_colstats(const float* x, int64_t rows, int32_t C, int64_t ld, float* mean, float* var,
+                     float* running_mean, float* running_var, float momentum, double* partial,
+                     cartnet_stream_t stream);
+
+/* out[C] (fp32) = column sums of x[rows, C] (T or fp32 selected by x_is_t/prec). */
+int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld,
+                   float* out, double* partial, cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused edge / node passes of CartNet_layer (cartnet.py:230-274) and their backward.
+ * D = dim_in (multiple of 4). Edges are dst-sorted; row_ptr is the dst CSR.
+ * bn_*: mean/var are the batch statistics (train) or the running ones (eval), eps = 1e-5.
+ * ------------------------------------------------------------------------------------- */
+
+/* Forward edge pass:  ghat = BN(g); sig = env(dist) * sigmoid(ghat); e_out = e + sig;
+ * m[i] = sum_{edges -> i, CSR order} sig * s   (deterministic, no atomics).
+ * env(d) = 0.5 (cos(pi d / radius) + 1) (d < radius) when use_envelope else 1.
+ * e_out_t (T shadow for the next layer's GEMM operand) may be null. */
+int cartnet_edge_gate_aggregate(const float* g, const float* s, const float* e, const float* dist,
+                                const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
+                                const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                const float* bn_bias, float eps, float radius, int32_t use_envelope,
+                                float* e_out, void* e_out_t, int32_t prec, float* m,
+                                cartnet_stream_t stream);
+
+/* Forward node pass: x_out = silu(BN2(m)) + x ; x_out_t optional T shadow. */
+int cartnet_node_update(const float* m, const float* x, int32_t num_nodes, int32_t D,
+                        const float* bn_mean, const float* bn_var, const float* bn_weight,
+                        const float* bn_bias, float eps, float* x_out, void* x_out_t, int32_t prec,
+                        cartnet_stream_t stream);
+
+/* Backward node pass, step 1: dy = dx_out * silu'(BN2(m)); sums[0:D] = sum_n dy,
+ * sums[D:2D] = sum_n dy * yhat   (yhat = (m-mean)*rstd). fp64 partial scratch as in colstats. */
+int cartnet_node_update_bwd_reduce(const float* dx_out, const float* m, int32_t num_nodes, int32_t D,
+                                   const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                   const float* bn_bias, float eps, float* sums, double* partial,
+                                   cartnet_stream_t stream);
+/* step 2: dm = weight*rstd*(dy - [train](sum_dy/N + yhat*sum_dy_yhat/N)); writes dm[N,D].
+ * training = 0 gives the affine (eval-mode) backward. */
+int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t num_nodes, int32_t D,
+                                  const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                  const float* bn_bias, float eps, const float* sums, int32_t training,
+                                  float* dm, cartnet_stream_t stream);
+
+/* Backward edge pass, step 1 (per edge, channel):  dmd = dm[dst];  ds = sig * dmd  -> ds_t (T);
+ * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat (fp32);
+ * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm. */
+int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
+                                 const float* de_out, const float* dm, int64_t num_edges, int32_t D,
+                                 const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                 const float* bn_bias, float eps, float radius, int32_t use_envelope,
+                                 void* ds_t, float* dghat, int32_t prec, float* sums, double* partial,
+                                 cartnet_stream_t stream);
+/* step 2: dg = weight*rstd*(dghat - [train](sum/E + ghat_norm*sum2/E)) -> dg_t (T). */
+int cartnet_edge_gate_bwd_apply(const float* g, const float* dghat, int64_t num_edges, int32_t D,
+                                const float* bn_mean, const float* bn_var, const float* bn_weight,
+                                float eps, const float* sums, int32_t training, void* dg_t, int32_t prec,
+                                cartnet_stream_t stream);
+
+/* out[n, 0:C] = sum over CSR row n of x[perm[k], 0:C] (perm may be null = identity). x is T,
+ * out is T (out_is_t=1) or fp32. Used for d(P_i) (dst CSR) and d(P_j) (src CSR) -- the transpose of the
+ * lifts at cartnet.py:218-221. Fixed order => deterministic. */
+int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const int32_t* perm,
+                        int32_t num_nodes, int32_t C, void* out, int64_t ldo, int32_t out_is_t,
+                        int32_t prec, cartnet_stream_t stream);
+
+/* y_t = (T)(dy * silu'(z)) elementwise over [rows, C]; dy fp32 (ld_dy), z T (ldz), y T (ldy). */
+int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy,
+                      int64_t rows, int32_t C, int32_t prec, cartnet_stream_t stream);
+
+/* dst_t = (T) src  over [rows, C]. */
+int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C,
+                      int32_t prec, cartnet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARTNET_B200_H */

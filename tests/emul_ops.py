@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE ONLY: plain-torch executable specification of every primitive in
+cartnet_b200/ops.py (same names, same signatures, same in-place conventions).
+
+Two uses:
+  * CPU tests monkeypatch `cartnet_b200.ops` with these functions to check the HOST logic
+    (weight packing, the hand-derived backward composition, BatchNorm buffer updates, shadow
+    plumbing) against the oracle without a GPU;
+  * GPU tests compare each CUDA primitive against the function of the same name here.
+The product never imports this module.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_FP32, GraphPlan, f32_storage, t_dtype  # noqa: F401
+
+EPS_BN = 1e-5
+
+
+def _f(t):
+    return t.to(torch.float64) if HIGH else t.to(torch.float32)
+
+
+HIGH = False   # set True to emulate in fp64 (tolerance budgeting)
+
+
+def _dsilu(z):
+    s = torch.sigmoid(z)
+    return s * (1 + z * (1 - s))
+
+
+def _env(dist, radius, use_envelope):
+    if not use_envelope:
+        return torch.ones_like(dist)
+    return 0.5 * (torch.cos(dist * math.pi / radius) + 1.0) * (dist < radius)
+
+
+def _bn(x, mean, var, w, b):
+    rstd = 1.0 / torch.sqrt(var + EPS_BN)
+    xhat = (x - mean) * rstd
+    return xhat * w + b, xhat, rstd
+
+
+def graph_plan(edge_index, num_nodes):
+    E = edge_index.shape[1]
+    src, dst = edge_index[0], edge_index[1]
+    if ((src < 0) | (src >= num_nodes) | (dst < 0) | (dst >= num_nodes)).any():
+        raise IndexError("edge_index out of range")
+    perm_dst = None
+    if E > 1 and (dst[1:] < dst[:-1]).any():
+        perm_dst = torch.sort(dst, stable=True)[1]
+        src, dst = src[perm_dst], dst[perm_dst]
+
+    def csr(keys):
+        perm = torch.sort(keys, stable=True)[1].to(torch.int32)
+        ptr = torch.zeros(num_nodes + 1, dtype=torch.int32)
+        ptr[1:] = torch.cumsum(torch.bincount(keys, minlength=num_nodes), 0).to(torch.int32)
+        return ptr, perm
+    row_ptr, _ = csr(dst)
+    col_ptr, perm_src = csr(src)
+    return GraphPlan(num_nodes, E, src.to(torch.int32), dst.to(torch.int32), row_ptr, col_ptr, perm_src, perm_dst)
+
+
+def edge_features(cart_dist, cart_dir, means, betas, cutoff_upper, invariant, ld, prec):
+    d = cart_dist.unsqueeze(-1)
+    alpha = 5.0 / cutoff_upper
+    cut = 0.5 * (torch.cos(d * math.pi / cutoff_upper) + 1.0) * (d < cutoff_upper)
+    rbf = cut * torch.exp(-betas * (torch.exp(alpha * (-d)) - means) ** 2)
+    parts = [rbf] if invariant else [rbf, cart_dir]
+    feat = torch.cat(parts, dim=-1)
+    feat = F.pad(feat, (0, ld - feat.shape[1]))
+    return feat.to(t_dtype(prec))
+
+
+def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1=None, z_out=None,
+         act=ACT_NONE, z_in=None, resid=None, out_f32=None, out_t=None):
+    v = _f(A) @ _f(B).t()
+    if bias is not None:
+        v = v + _f(bias)
+    if gather0 is not None:
+        v = v + _f(gather0)[gidx0.long()]
+    if gather1 is not None:
+        v = v + _f(gather1)[gidx1.long()]
+    if z_out is not None:
+        z_out.copy_(v.to(z_out.dtype))
+    if act == ACT_SILU:
+        v = F.silu(v)
+    elif act == ACT_MUL_DSILU:
+        v = v * _dsilu(_f(z_in))
+    if resid is not None:
+        v = v + _f(resid)
+    if out_f32 is not None:
+        out_f32.copy_(v.to(torch.float32))
+    if out_t is not None:
+        out_t.copy_(v.to(out_t.dtype))
+
+
+def gemm_tn(prec, A, B):
+    return (_f(A).t() @ _f(B)).to(torch.float32)
+
+
+def colstats(x, running_mean=None, running_var=None, momentum=0.1):
+    xx = x.to(torch.float64)
+    n = x.shape[0]
+    mean = xx.mean(0)
+    var = (xx * xx).mean(0) - mean * mean
+    var = var.clamp(min=0)
+    if running_mean is not None:
+        unb = var * n / (n - 1) if n > 1 else var
+        running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * mean).float())
+        running_var.copy_(((1 - momentum) * running_var.double() + momentum * unb).float())
+    return mean.float(), var.float()
+
+
+def colsum(x, prec):
+    return x.to(torch.float64).sum(0).float()
+
+
+def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes, bn_mean, bn_var, bn_w, bn_b, radius, use_envelope, prec,
+                        want_shadow):
+    ghat, _, _ = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+    sig = _env(_f(dist), radius, use_envelope).unsqueeze(-1) * torch.sigmoid(ghat)
+    e_out = (_f(e) + sig).float()
+    counts = (row_ptr[1:] - row_ptr[:-1]).long()
+    dst = torch.repeat_interleave(torch.arange(num_nodes), counts)
+    m = torch.zeros(num_nodes, e.shape[1], dtype=sig.dtype).index_add_(0, dst, sig * _f(s)).float()
+    e_t = e_out if f32_storage(prec) else e_out.to(t_dtype(prec))
+    return e_out, e_t, m
+
+
+def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec, want_shadow):
+    y, _, _ = _bn(_f(m), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+    x_out = (F.silu(y) + _f(x)).float()
+    return x_out, (x_out if f32_storage(prec) else x_out.to(t_dtype(prec)))
+
+
+def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training):
+    y, yhat, rstd = _bn(_f(m), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+    dy = _f(dx_out) * _dsilu(y)
+    s1, s2 = dy.sum(0), (dy * yhat).sum(0)
+    n = m.shape[0]
+    corr = (s1 / n + yhat * s2 / n) if training else 0.0
+    dm = _f(bn_w) * rstd * (dy - corr)
+    return dm.float(), torch.cat([s1, s2]).float()
+
+
+def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, radius, use_envelope, training, prec):
+    ghat, gn, rstd = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+    sg = torch.sigmoid(ghat)
+    env = _env(_f(dist), radius, use_envelope).unsqueeze(-1)
+    dmd = _f(dm)[dst32.long()]
+    ds = env * sg * dmd
+    dghat = (_f(de_out) + _f(s) * dmd) * env * sg * (1 - sg)
+    s1, s2 = dghat.sum(0), (dghat * gn).sum(0)
+    n = g.shape[0]
+    corr = (s1 / n + gn * s2 / n) if training else 0.0
+    dg = _f(bn_w) * rstd * (dghat - corr)
+    T = t_dtype(prec)
+    return ds.to(T), dg.to(T), torch.cat([s1, s2]).float()
+
+
+def segment_sum(x, ptr, perm, num_nodes, out, prec):
+    counts = (ptr[1:] - ptr[:-1]).long()
+    seg = torch.repeat_interleave(torch.arange(num_nodes), counts)
+    rows = _f(x) if perm is None else _f(x)[perm.long()]
+    res = torch.zeros(num_nodes, x.shape[1], dtype=rows.dtype).index_add_(0, seg, rows)
+    out.copy_(res.to(out.dtype))
+    return out
+
+
+def dsilu_mul(dy, z, prec):
+    return (_f(dy) * _dsilu(_f(z))).to(t_dtype(prec))
+
+
+def cast(x, prec):
+    return x if f32_storage(prec) else x.to(t_dtype(prec))
+
+
+ALL = ["graph_plan", "edge_features", "gemm", "gemm_tn", "colstats", "colsum", "edge_gate_aggregate", "node_update",
+       "node_update_bwd", "edge_gate_bwd", "segment_sum", "dsilu_mul", "cast"]
+
+
+def install(monkeypatch):
+    """Route cartnet_b200.ops through this module (CPU host-logic tests only)."""
+    import sys
+    from cartnet_b200 import ops
+    me = sys.modules[__name__]
+    for name in ALL:
+        monkeypatch.setattr(ops, name, getattr(me, name))

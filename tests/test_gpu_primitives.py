@@ -1,0 +1,200 @@
+"""GPU: every CUDA primitive against its plain-torch specification (tests/emul_ops.py) on seeded inputs,
+called through the C ABI (cartnet_b200/ops.py -> ctypes -> libcartnet_b200.so)."""
+import numpy as np
+import pytest
+import torch
+
+import common
+import emul_ops as EM
+from cartnet_b200 import ops
+from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_FP32
+
+pytestmark = pytest.mark.gpu
+
+PRECS = [PREC_FP32, PREC_BF16]
+
+
+def tol(prec):
+    return 2e-5 if prec == PREC_FP32 else 1.5e-2
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed + 1000 * len(shape) + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def both(fn_name, args_cpu, kw_cpu=None):
+    kw_cpu = kw_cpu or {}
+    to = lambda v: v.cuda() if torch.is_tensor(v) else v
+    ref = getattr(EM, fn_name)(*args_cpu, **kw_cpu)
+    got = getattr(ops, fn_name)(*[to(a) for a in args_cpu], **{k: to(v) for k, v in kw_cpu.items()})
+    return ref, got
+
+
+def test_edge_features_golden(golden_feat):
+    d = torch.from_numpy(golden_feat["dist"]).cuda()
+    means, betas = torch.from_numpy(golden_feat["means"]).cuda(), torch.from_numpy(golden_feat["betas"]).cuda()
+    cdir = torch.nn.functional.normalize(rnd(d.numel(), 3), dim=-1).cuda()
+    f = ops.edge_features(d, cdir, means, betas, 5.0, False, 68, PREC_FP32)
+    ref = torch.from_numpy(golden_feat["rbf"])
+    assert float((f[:, :64].cpu() - ref).abs().max()) < 2e-6          # reference RBF values, absolute (values in [0,1])
+    assert torch.equal(f[:, 64:67], cdir) and float(f[:, 67:].abs().max()) == 0.0
+    f2 = ops.edge_features(d, None, means, betas, 5.0, True, 64, PREC_FP32)
+    assert torch.equal(f2, f[:, :64])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (77, 256, 256), (4096 + 33, 256, 512), (300, 1024, 256), (513, 512, 128)])
+def test_gemm_plain(prec, M, N, K):
+    T = ops.t_dtype(prec)
+    A, B = rnd(M, K, seed=1).to(T), rnd(N, K, seed=2, scale=K ** -0.5).to(T)
+    out = torch.empty(M, N, dtype=torch.float32)
+    EM.gemm(prec, A, B, out_f32=out)
+    outg = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(prec, A.cuda(), B.cuda(), out_f32=outg)
+    assert common.rel_err(outg, out) < (2e-6 if prec == PREC_FP32 else 1e-5)   # same rounded operands, fp32 accumulate
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gemm_fused_epilogues(prec):
+    T = ops.t_dtype(prec)
+    M, N, K, NN = 1500, 512, 256, 211
+    A, B = rnd(M, K, seed=1).to(T), rnd(N, K, seed=2, scale=K ** -0.5).to(T)
+    bias = rnd(N, seed=3)
+    P = rnd(NN, 2 * N, seed=4).to(T)
+    g = torch.Generator().manual_seed(9)
+    i0 = torch.randint(0, NN, (M,), generator=g, dtype=torch.int32)
+    i1 = torch.randint(0, NN, (M,), generator=g, dtype=torch.int32)
+    resid = rnd(M, N, seed=5)
+    zin = rnd(M, N, seed=6).to(T)
+    big = torch.zeros(M, 2 * N, dtype=T)       # strided output views (ldt = 2N)
+
+    def run(mod, dev):
+        mv = lambda t: t.to(dev)
+        outs = {}
+        # (1) edge-GEMM-1 style: bias + two gathers, store z, silu, store T
+        z, h = torch.empty(M, N, dtype=T, device=dev), torch.empty(M, N, dtype=T, device=dev)
+        mod.gemm(prec, mv(A), mv(B), bias=mv(bias), gather0=mv(P)[:, :N], gidx0=mv(i0), gather1=mv(P)[:, N:], gidx1=mv(i1),
+                 z_out=z, act=ACT_SILU, out_t=h)
+        outs["z"], outs["h"] = z, h
+        # (2) dgrad style: * silu'(z_in), strided T output
+        bb = mv(big).clone()
+        mod.gemm(prec, mv(A), mv(B), act=ACT_MUL_DSILU, z_in=mv(zin), out_t=bb[:, N:])
+        outs["dz"] = bb
+        # (3) residual + fp32 out, A given as a strided column view
+        A2 = mv(torch.cat([A, A], dim=1))
+        o = torch.empty(M, N, dtype=torch.float32, device=dev)
+        mod.gemm(prec, A2[:, K:], mv(B), resid=mv(resid), out_f32=o)
+        outs["res"] = o
+        return outs
+    ref, got = run(EM, "cpu"), run(ops, "cuda")
+    for k in ref:
+        assert common.rel_err(got[k].float(), ref[k].float()) < (3e-6 if prec == PREC_FP32 else 1e-2), k
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("K,M,N", [(5000, 512, 256), (333, 256, 256), (70001, 256, 512), (1200, 1024, 256), (900, 512, 128)])
+def test_gemm_tn(prec, K, M, N):
+    T = ops.t_dtype(prec)
+    A, B = rnd(K, M, seed=1).to(T), rnd(K, N, seed=2).to(T)
+    big = torch.cat([A, A], dim=1)
+    ref = EM.gemm_tn(prec, A, B)
+    got = ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda())
+    assert common.rel_err(got, ref) < 5e-6
+    got2 = ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda())
+    assert torch.equal(got, got2)                      # deterministic split-K
+
+
+def test_colstats_and_running_update():
+    x = rnd(30011, 256, seed=1) * 0.01 + 3.0           # |mean| >> std: the cancellation-prone case
+    rm, rv = rnd(256, seed=2), rnd(256, seed=3).abs() + 0.5
+    rm_g, rv_g = rm.cuda(), rv.cuda()
+    mean, var = EM.colstats(x, rm, rv, 0.1)
+    mg, vg = ops.colstats(x.cuda(), rm_g, rv_g, 0.1)
+    assert common.rel_err(mg, mean) < 1e-6 and common.rel_err(vg, var) < 1e-4
+    assert common.rel_err(rm_g, rm) < 1e-6 and common.rel_err(rv_g, rv) < 1e-6
+    ref = torch.nn.functional.batch_norm(x, None, None, training=True)           # torch's own batch statistics
+    mine = (x - mg.cpu()) / torch.sqrt(vg.cpu() + 1e-5)
+    assert float((ref - mine).abs().max()) < 2e-3 * float(ref.abs().max())
+    assert common.rel_err(ops.colsum(x.cuda(), PREC_FP32), x.double().sum(0).float()) < 1e-6
+
+
+def _bn_args(D, seed):
+    return rnd(D, seed=seed) * 0.3, rnd(D, seed=seed + 1).abs() * 0.5 + 0.2, rnd(D, seed=seed + 2) * 0.2 + 1.0, rnd(D, seed=seed + 3) * 0.2
+
+
+def _graph(N, E, seed):
+    g = torch.Generator().manual_seed(seed)
+    dst = torch.sort(torch.randint(0, N, (E,), generator=g))[0]
+    dst[dst == 3] = 4                                       # leave node 3 without in-edges
+    src = torch.randint(0, N, (E,), generator=g)
+    return EM.graph_plan(torch.stack([src, dst]), N)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("use_env", [True, False])
+def test_edge_gate_aggregate(prec, use_env):
+    N, E, D = 301, 17011, 256
+    plan = _graph(N, E, 1)
+    g, s, e = rnd(E, D, seed=1), rnd(E, D, seed=2), rnd(E, D, seed=3)
+    dist = torch.rand(E, generator=torch.Generator().manual_seed(4)) * 5.5
+    mean, var, w, b = _bn_args(D, 5)
+    ref, got = both("edge_gate_aggregate", (g, s, e, dist, plan.row_ptr, N, mean, var, w, b, 5.0, use_env, prec, True))
+    assert common.rel_err(got[0], ref[0]) < 2e-6
+    assert common.rel_err(got[1].float(), ref[1].float()) < (2e-6 if prec == PREC_FP32 else 8e-3)
+    assert common.rel_err(got[2], ref[2]) < 1e-5
+    assert float(got[2][3].abs().max()) == 0.0             # node without in-edges gets exactly 0
+    got2 = ops.edge_gate_aggregate(g.cuda(), s.cuda(), e.cuda(), dist.cuda(), plan.row_ptr.cuda(), N, mean.cuda(), var.cuda(),
+                                   w.cuda(), b.cuda(), 5.0, use_env, prec, True)
+    assert torch.equal(got2[2], got[2])                    # deterministic reduction
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_node_update_fwd_bwd(training):
+    N, D = 1234, 256
+    m, x, dx = rnd(N, D, seed=1), rnd(N, D, seed=2), rnd(N, D, seed=3)
+    mean, var, w, b = _bn_args(D, 7)
+    ref, got = both("node_update", (m, x, mean, var, w, b, PREC_BF16, True))
+    assert common.rel_err(got[0], ref[0]) < 2e-6 and common.rel_err(got[1].float(), ref[1].float()) < 8e-3
+    ref, got = both("node_update_bwd", (dx, m, mean, var, w, b, training))
+    assert common.rel_err(got[0], ref[0]) < 1e-5 and common.rel_err(got[1], ref[1]) < 1e-5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("training", [True, False])
+def test_edge_gate_bwd(prec, training):
+    N, E, D = 150, 9001, 256
+    plan = _graph(N, E, 2)
+    g, s, de = rnd(E, D, seed=1), rnd(E, D, seed=2), rnd(E, D, seed=3)
+    dm = rnd(N, D, seed=4)
+    dist = torch.rand(E, generator=torch.Generator().manual_seed(4)) * 5.5
+    mean, var, w, b = _bn_args(D, 5)
+    ref, got = both("edge_gate_bwd", (g, s, dist, plan.dst32, de, dm, mean, var, w, b, 5.0, True, training, prec))
+    t = 1e-5 if prec == PREC_FP32 else 8e-3
+    assert common.rel_err(got[0].float(), ref[0].float()) < t
+    assert common.rel_err(got[1].float(), ref[1].float()) < t
+    assert common.rel_err(got[2], ref[2]) < 1e-5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_segment_sum_dst_and_src(prec):
+    N, E, C = 97, 6007, 512
+    plan = _graph(N, E, 3)
+    T = ops.t_dtype(prec)
+    x = rnd(E, C, seed=1).to(T)
+    for ptr, perm in ((plan.row_ptr, None), (plan.col_ptr, plan.perm_src)):
+        ref = EM.segment_sum(x, ptr, perm, N, torch.empty(N, 2 * C, dtype=T)[:, C:], prec)
+        out = torch.zeros(N, 2 * C, dtype=T, device="cuda")
+        got = ops.segment_sum(x.cuda(), ptr.cuda(), None if perm is None else perm.cuda(), N, out[:, C:], prec)
+        assert common.rel_err(got.float(), ref.float()) < (1e-5 if prec == PREC_FP32 else 8e-3)
+        assert float(out[:, :C].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_elementwise(prec):
+    T = ops.t_dtype(prec)
+    dy, z = rnd(777, 512, seed=1), rnd(777, 512, seed=2).to(T)
+    ref, got = both("dsilu_mul", (dy, z, prec))
+    assert common.rel_err(got.float(), ref.float()) < (2e-6 if prec == PREC_FP32 else 8e-3)
+    ref, got = both("cast", (dy, prec))
+    assert torch.equal(got.cpu(), ref)
