@@ -31,11 +31,14 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
     const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
     const int ty = tid >> 4, tx = tid & 15;
 
-    float acc[8][8];
+    // Parity path: every 16-wide K block is accumulated in fp32 (chain length 16) and the running total is
+    // carried in fp64, so the rounding error does not grow with K (the reference's MKL sgemm also keeps many
+    // short partial sums). Costs ~15% and registers; this is the 1e-5 path, not the fast one.
+    double dacc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) dacc[i][j] = 0.0;
 
     float4 ra[2], rb[2];
     auto load_tile = [&](int64_t k0) {
@@ -76,6 +79,11 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
         store_tile();
         __syncthreads();
         if (k0 + BK < ke) load_tile(k0 + BK);
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -89,6 +97,10 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dacc[i][j] += (double)acc[i][j];
         __syncthreads();
     }
 
@@ -102,7 +114,7 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
         for (int jh = 0; jh < 2; ++jh) {
             const int col = n0 + jh * 64 + tx * 4;
             if (col >= N) continue;   // N % 4 == 0 is required, so a float4 never straddles N
-            float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            float4 v = make_float4((float)dacc[i][jh * 4 + 0], (float)dacc[i][jh * 4 + 1], (float)dacc[i][jh * 4 + 2], (float)dacc[i][jh * 4 + 3]);
             if (MODE == 0) {
                 epi_apply4(epi, er, (int64_t)row, col, v);
             } else {

@@ -1,7 +1,516 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM / TMA GEMMs for sm_100a (CARTNET_PREC_BF16: kind::f16 on bf16 operands,
+// CARTNET_PREC_TF32: kind::tf32 reading the fp32 tensors directly). Hand-written PTX; descriptor bit
+// layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
+//
+// NT kernel  C[M,N] = A[M,K] B[N,K]^T  (+ fused epilogue, gemm_epilogue.cuh)
+//   * persistent, one CTA per SM; the CTA's 128 KB weight slice B[n0:n0+BN, 0:K] is loaded ONCE by TMA and
+//     stays resident in shared memory (K-major, 128B swizzle), so per 128-row tile only A streams through a
+//     4-stage TMA/mbarrier ring (16 KB per stage) -- weights never re-cross L2->SM per tile;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread, tcgen05.mma cta_group::1, M=128, N=BN),
+//     warps 2..9 = epilogue: tcgen05.ld 32 columns at a time from one of TWO TMEM accumulators, so the
+//     epilogue of tile i overlaps the MMAs of tile i+1; gathers / bias / SiLU / stores are fused there.
+//
+// TN kernel  C[M,N] = sum_k A[k,M]^T B[k,N]  (weight gradients; K = edges or nodes, split over CTAs)
+//   * both operands are MN-major as they lie in HBM ([k, mn] row-major), fed by TMA boxes of
+//     [kblock rows x 128 bytes] straight into the canonical MN-major 128B-swizzle layout -- no transposes;
+//   * each CTA owns a 256 x Nblk output block (two M=128 accumulators = up to 512 TMEM columns) and a
+//     contiguous K range; partial blocks go to a workspace and are summed in a fixed order (deterministic).
+#include <cuda.h>
+
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
+
 namespace cartnet {
-int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st) { set_error("bf16 tcgen05 GEMM not built yet"); return 3; }
-int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, float* ws, int64_t ws_bytes, cudaStream_t st) { set_error("bf16 tcgen05 GEMM not built yet"); return 3; }
-int64_t gemm_tc_tn_workspace(int prec, int M, int N, int64_t K) { return 16; }
+
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int64_t ldc, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = output row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a_format [7,10), b_format [10,13)
+// (BF16 = 1, TF32 = 2), a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ inline uint32_t instr_desc(int fmt, int a_mn_major, int b_mn_major, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <typename T>
+struct TcTraits;
+template <>
+struct TcTraits<__nv_bfloat16> {
+    static constexpr int KB = 64;        // elements per 128-byte swizzle row
+    static constexpr int UMMA_K = 16;
+    static constexpr int FMT = 1;
+    static constexpr bool TF32 = false;
+    static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    // MN-major operands (TN kernel): canonical SWIZZLE_128B atom = 8 k rows x 128 B
+    static constexpr uint32_t MN_LAYOUT = 2, MN_SBO = 1024;
+    static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B;
+};
+template <>
+struct TcTraits<float> {
+    static constexpr int KB = 32;
+    static constexpr int UMMA_K = 8;
+    static constexpr int FMT = 2;
+    static constexpr bool TF32 = true;
+    static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    // 32-bit MN-major operands only exist as SWIZZLE_128B_BASE32B (Swizzle<2,5,2>): atom = 4 k rows x 128 B,
+    // 32-byte chunks XORed with the row index; TMA writes it with SWIZZLE_128B_ATOM_32B
+    static constexpr uint32_t MN_LAYOUT = 1, MN_SBO = 512;
+    static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+};
+
+// ------------------------------------------------------------------------------------------ NT kernel
+constexpr int NT_STAGES = 4;
+constexpr int NT_A_STAGE_BYTES = 128 * 128;      // 128 rows x 128 B
+constexpr int NT_EPI_WARPS = 8;
+constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
+
+struct NtBars {
+    uint64_t a_full[NT_STAGES], a_empty[NT_STAGES], b_full, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_slot;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT_THREADS, 1)
+tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+             int BN, int n_tiles, int m_tiles, EpiParams<T> epi) {
+    using TR = TcTraits<T>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int kblks = K / TR::KB;
+    const int b_kb_bytes = BN * 128;
+    uint8_t* smemB = smem;
+    uint8_t* smemA = smem + (size_t)kblks * b_kb_bytes;
+    NtBars* bars = reinterpret_cast<NtBars*>(smemA + NT_STAGES * NT_A_STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x % n_tiles;
+    const int m_first = blockIdx.x / n_tiles, m_stride = gridDim.x / n_tiles;
+    const int n0 = n_tile * BN;
+    const uint32_t tmem_cols = (uint32_t)(2 * BN < 32 ? 32 : 2 * BN);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NT_STAGES; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
+        mbar_init(&bars->b_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], NT_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(&bars->b_full, (uint32_t)(kblks * b_kb_bytes));
+            for (int kb = 0; kb < kblks; ++kb) tma_load_2d(smemB + (size_t)kb * b_kb_bytes, &tmB, kb * TR::KB, n0, &bars->b_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mt = m_first; mt < m_tiles; mt += m_stride) {
+                for (int kb = 0; kb < kblks; ++kb) {
+                    mbar_wait(&bars->a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bars->a_full[stage], NT_A_STAGE_BYTES);
+                    tma_load_2d(smemA + stage * NT_A_STAGE_BYTES, &tmA, kb * TR::KB, mt * 128, &bars->a_full[stage]);
+                    if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        const uint32_t idesc = instr_desc(TR::FMT, 0, 0, 128, BN);
+        mbar_wait(&bars->b_full, 0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int mt = m_first; mt < m_tiles; mt += m_stride) {
+            mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < kblks; ++kb) {
+                mbar_wait(&bars->a_full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smemA + stage * NT_A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(smemB + (size_t)kb * b_kb_bytes);
+#pragma unroll
+                    for (int j = 0; j < TR::KB / TR::UMMA_K; ++j) {   // 4 MMAs of K = 32 bytes inside the swizzle row
+                        const uint64_t ad = smem_desc(a_addr + j * 32, 16, 1024);
+                        const uint64_t bd = smem_desc(b_addr + j * 32, 16, 1024);
+                        tc_mma<TR::TF32>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&bars->a_empty[stage]);                  // frees the A stage when the MMAs retire
+                    if (kb == kblks - 1) tc_commit(&bars->tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        // ------------------------------------------------ epilogue: TMEM -> registers -> fused epilogue -> HBM
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;              // column group (0/1)
+        const int cols_per_grp = (BN / 2) < 32 ? 32 : (BN / 2);
+        const int c_begin = grp * cols_per_grp;
+        const int c_end = (c_begin + cols_per_grp) < BN ? (c_begin + cols_per_grp) : BN;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int mt = m_first; mt < m_tiles; mt += m_stride) {
+            mbar_wait(&bars->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int64_t row = (int64_t)mt * 128 + q * 32 + lane;
+            const bool valid = row < M;
+            EpiRow<T> er;
+            er.g0 = nullptr; er.g1 = nullptr;
+            if (valid) er = epi_row(epi, row);
+            for (int c = c_begin; c < c_end; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (valid) {
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq)
+                        epi_apply4(epi, er, row, n0 + c + 4 * gq, make_float4(v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ TN kernel
+constexpr int TN_STAGES = 3;
+constexpr int TN_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int TN_MBLK = 256;
+
+struct TnBars {
+    uint64_t full[TN_STAGES], empty[TN_STAGES], tmem_full;
+    uint32_t tmem_slot;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t K, int M, int N,
+             int Nblk, int n_blocks, int kblks_total, int kblks_per_split, float* __restrict__ partial) {
+    using TR = TcTraits<T>;
+    constexpr int BOXW = TR::KB;                    // mn elements per 128-byte row
+    constexpr int KROWS = TR::KB;                   // k rows per stage: 64 (bf16) / 32 (tf32)
+    constexpr int BOX_BYTES = KROWS * 128;
+    constexpr int A_BOXES = TN_MBLK / BOXW;
+    constexpr int A_BYTES = A_BOXES * BOX_BYTES;    // 32 KB
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_boxes = Nblk / BOXW;
+    const int stage_bytes = A_BYTES + b_boxes * BOX_BYTES;
+    TnBars* bars = reinterpret_cast<TnBars*>(smem + (size_t)TN_STAGES * stage_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int mb = blockIdx.y / n_blocks, nb = blockIdx.y % n_blocks;
+    const int kb0 = split * kblks_per_split;
+    const int kb1 = (kb0 + kblks_per_split) < kblks_total ? (kb0 + kblks_per_split) : kblks_total;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * Nblk)) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + A_BYTES;
+                for (int i = 0; i < A_BOXES; ++i) tma_load_2d(sa + i * BOX_BYTES, &tmA, mb * TN_MBLK + i * BOXW, kb * KROWS, &bars->full[stage]);
+                for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * BOX_BYTES, &tmB, nb * Nblk + i * BOXW, kb * KROWS, &bars->full[stage]);
+                if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = instr_desc(TR::FMT, 1, 1, 128, Nblk);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int j = 0; j < KROWS / TR::UMMA_K; ++j) {
+                    // MN-major canonical layout: LBO = distance between 128-byte-wide MN chunks (one TMA box),
+                    // SBO = distance between swizzle atoms along k (8 rows bf16 / 4 rows tf32); UMMA_K rows = UMMA_K * 128 bytes
+                    const uint32_t koff = (uint32_t)(j * TR::UMMA_K * 128);
+                    const uint64_t bd = smem_desc(b_addr + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t ad = smem_desc(a_addr + h * (A_BYTES / 2) + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
+                        tc_mma<TR::TF32>(tmem_base + (uint32_t)(h * Nblk), ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&bars->empty[stage]);
+                if (kb == kb1 - 1) tc_commit(&bars->tmem_full);
+            }
+            __syncwarp();
+            if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(&bars->tmem_full, 0);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+            const int row = mb * TN_MBLK + h * 128 + q * 32 + lane;
+            float* dst = partial + ((int64_t)split * M + row) * N + (int64_t)nb * Nblk;
+            for (int c = 0; c < Nblk; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * Nblk + c), v);
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq)
+                    *reinterpret_cast<float4*>(dst + c + 4 * gq) = make_float4(v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols], 128B swizzle
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
+                    int64_t ld, int box_cols, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * esize) & 15)) {
+        set_error("tcgen05 GEMM operand must be 16-byte aligned with a 16-byte-multiple row pitch");
+        return 2;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld * esize)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)", (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols); return 1; }
+    return 0;
+}
+
+template <typename T>
+static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
+    using TR = TcTraits<T>;
+    const int esize = (int)sizeof(T);
+    CN_CHECK_ARG(d.K % TR::KB == 0, "tcgen05 gemm: K=%d must be a multiple of %d", d.K, TR::KB);
+    // resident weight slice: largest BN with BN*K*esize <= 128 KB that divides N
+    int BN = 0;
+    for (int cand : {256, 128, 64, 32})
+        if ((int64_t)cand * d.K * esize <= 131072 && d.N % cand == 0) { BN = cand; break; }
+    CN_CHECK_ARG(BN > 0, "tcgen05 gemm: no resident tile for N=%d K=%d", d.N, d.K);
+    const int n_tiles = d.N / BN, m_tiles = ceil_div(d.M, 128);
+    CN_CHECK_ARG(n_tiles <= kNumSMs, "tcgen05 gemm: too many N tiles (%d)", n_tiles);
+    int grid = (kNumSMs / n_tiles) * n_tiles;
+    if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, TR::DT, esize, d.A, d.M, d.K, d.lda, TR::KB, 128);
+    if (rc) return rc;
+    rc = make_map(&tmB, TR::DT, esize, d.B, d.N, d.K, d.ldb, TR::KB, BN);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + sizeof(NtBars) + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    tc_nt_kernel<T><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, make_epi<T>(d));
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st) {
+    if (d.prec == CARTNET_PREC_BF16) return run_nt<__nv_bfloat16>(d, st);
+    return run_nt<float>(d, st);
+}
+
+struct TnPlan {
+    int Nblk, n_blocks, m_blocks, kblks_total, kblks_per_split, splits;
+};
+static bool tn_plan(int prec, int M, int N, int64_t K, TnPlan* p) {
+    const int boxw = prec == CARTNET_PREC_BF16 ? 64 : 32;
+    if (M % TN_MBLK != 0 || N % boxw != 0) return false;
+    p->Nblk = N <= 256 ? N : 256;
+    if (N % p->Nblk != 0 || p->Nblk % 32 != 0 || p->Nblk % 16 != 0) return false;
+    p->n_blocks = N / p->Nblk;
+    p->m_blocks = M / TN_MBLK;
+    p->kblks_total = (int)ceil_div64(K > 0 ? K : 1, boxw);      // KROWS == boxw for both types
+    const int problems = p->n_blocks * p->m_blocks;
+    int s = kNumSMs / problems;
+    if (s < 1) s = 1;
+    if (s > p->kblks_total) s = p->kblks_total;
+    p->kblks_per_split = ceil_div(p->kblks_total, s);
+    p->splits = ceil_div(p->kblks_total, p->kblks_per_split);
+    return true;
+}
+
+int64_t gemm_tc_tn_workspace(int prec, int M, int N, int64_t K) {
+    TnPlan p;
+    if (!tn_plan(prec, M, N, K, &p)) return 16;
+    return (int64_t)p.splits * M * N * (int64_t)sizeof(float);
+}
+
+template <typename T>
+static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C,
+                  int64_t ldc, float* ws, cudaStream_t st) {
+    using TR = TcTraits<T>;
+    const int esize = (int)sizeof(T);
+    TnPlan p;
+    CN_CHECK_ARG(tn_plan(prec, M, N, K, &p), "tcgen05 gemm_tn: unsupported shape M=%d N=%d (need M %% 256 == 0, N %% %d == 0)", M, N, TR::KB);
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, TR::DT, esize, A, K, M, lda, TR::KB, TR::KB, TR::MN_SWIZZLE);
+    if (rc) return rc;
+    rc = make_map(&tmB, TR::DT, esize, B, K, N, ldb, TR::KB, TR::KB, TR::MN_SWIZZLE);
+    if (rc) return rc;
+    const int box_bytes = TR::KB * 128;
+    const size_t stage_bytes = (size_t)(TN_MBLK / TR::KB) * box_bytes + (size_t)(p.Nblk / TR::KB) * box_bytes;
+    const size_t smem = 1024 + TN_STAGES * stage_bytes + sizeof(TnBars) + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CN_CUDA(cudaFuncSetAttribute(tc_tn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    tc_tn_kernel<T><<<dim3(p.splits, p.m_blocks * p.n_blocks), TN_THREADS, smem, st>>>(
+        tmA, tmB, K, M, N, p.Nblk, p.n_blocks, p.kblks_total, p.kblks_per_split, ws);
+    CN_LAUNCH_CHECK();
+    return launch_splitk_reduce(ws, p.splits, M, N, C, ldc, st);
+}
+
+int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C,
+               int64_t ldc, float* ws, int64_t ws_bytes, cudaStream_t st) {
+    if (K <= 0) {
+        CN_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+        return 0;
+    }
+    if (prec == CARTNET_PREC_BF16) return run_tn<__nv_bfloat16>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
+    return run_tn<float>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
+}
+
+}  // namespace cartnet

@@ -7,11 +7,12 @@ import torch
 import common
 import emul_ops as EM
 from cartnet_b200 import ops
-from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_FP32
+from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32
 
 pytestmark = pytest.mark.gpu
 
 PRECS = [PREC_FP32, PREC_BF16]
+GEMM_PRECS = [PREC_FP32, PREC_BF16, PREC_TF32]     # TF32 shares every non-GEMM kernel with FP32 (T = float)
 
 
 def tol(prec):
@@ -43,7 +44,7 @@ def test_edge_features_golden(golden_feat):
     assert torch.equal(f2, f[:, :64])
 
 
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", GEMM_PRECS)
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (77, 256, 256), (4096 + 33, 256, 512), (300, 1024, 256), (513, 512, 128)])
 def test_gemm_plain(prec, M, N, K):
     T = ops.t_dtype(prec)
@@ -52,10 +53,11 @@ def test_gemm_plain(prec, M, N, K):
     EM.gemm(prec, A, B, out_f32=out)
     outg = torch.empty(M, N, dtype=torch.float32, device="cuda")
     ops.gemm(prec, A.cuda(), B.cuda(), out_f32=outg)
-    assert common.rel_err(outg, out) < (2e-6 if prec == PREC_FP32 else 1e-5)   # same rounded operands, fp32 accumulate
+    # fp32 / bf16: identical (rounded) operands, fp32 accumulation; tf32: the tensor core drops 13 mantissa bits
+    assert common.rel_err(outg, out) < {PREC_FP32: 2e-6, PREC_BF16: 1e-5, PREC_TF32: 2e-3}[prec]
 
 
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", GEMM_PRECS)
 def test_gemm_fused_epilogues(prec):
     T = ops.t_dtype(prec)
     M, N, K, NN = 1500, 512, 256, 211
@@ -92,7 +94,7 @@ def test_gemm_fused_epilogues(prec):
         assert common.rel_err(got[k].float(), ref[k].float()) < (3e-6 if prec == PREC_FP32 else 1e-2), k
 
 
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", GEMM_PRECS)
 @pytest.mark.parametrize("K,M,N", [(5000, 512, 256), (333, 256, 256), (70001, 256, 512), (1200, 1024, 256), (900, 512, 128)])
 def test_gemm_tn(prec, K, M, N):
     T = ops.t_dtype(prec)
@@ -100,7 +102,7 @@ def test_gemm_tn(prec, K, M, N):
     big = torch.cat([A, A], dim=1)
     ref = EM.gemm_tn(prec, A, B)
     got = ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda())
-    assert common.rel_err(got, ref) < 5e-6
+    assert common.rel_err(got, ref) < (2e-3 if prec == PREC_TF32 else 5e-6)
     got2 = ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda())
     assert torch.equal(got, got2)                      # deterministic split-K
 
