@@ -188,7 +188,20 @@ struct EdgeBwdF {
 // ------------------------------------------------------------------------------------------
 // forward edge pass: gate, residual, deterministic per-destination sum
 // ------------------------------------------------------------------------------------------
-template <typename T>
+// R = math type: double for the fp32 parity mode (the reference's own fp32 rounding already uses most of the
+// 1e-5 budget in training mode), float for the tensor-core modes.
+template <typename R> __device__ __forceinline__ R sigmoid_r(R v);
+template <> __device__ __forceinline__ float sigmoid_r<float>(float v) { return sigmoidf_(v); }
+template <> __device__ __forceinline__ double sigmoid_r<double>(double v) { return 1.0 / (1.0 + exp(-v)); }
+template <typename R> __device__ __forceinline__ R cutoff_r(float d, float upper);
+template <> __device__ __forceinline__ float cutoff_r<float>(float d, float upper) { return cosine_cutoff(d, upper); }
+template <> __device__ __forceinline__ double cutoff_r<double>(float d, float upper) {
+    // same operation order as models/utils.py:88 in fp32 for the argument, then a double cosine
+    const float arg = d * 3.14159265358979323846f / upper;
+    return d < upper ? 0.5 * (cos((double)arg) + 1.0) : 0.0;
+}
+
+template <typename T, typename R>
 __global__ void __launch_bounds__(256)
 edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict__ s, const float* __restrict__ e,
                            const float* __restrict__ dist, const int32_t* __restrict__ row_ptr, int num_nodes, int D,
@@ -199,26 +212,39 @@ edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict_
     const int node = blockIdx.x * npb + threadIdx.x / tpr;
     const int col = (threadIdx.x % tpr) * 4;
     if (node >= num_nodes) return;
-    const BnCoef c = bn_coef(mean, var, w, bias, eps, col);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    R mu[4], sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mu[j] = (R)mean[col + j];
+        const R rstd = (R)1 / sqrt((R)var[col + j] + (R)eps);
+        sc[j] = (w ? (R)w[col + j] : (R)1) * rstd;
+        sh[j] = bias ? (R)bias[col + j] : (R)0;
+    }
+    R acc[4] = {0, 0, 0, 0};
     const int k0 = row_ptr[node], k1 = row_ptr[node + 1];
     for (int k = k0; k < k1; ++k) {
         const int64_t o = (int64_t)k * D + col;
-        const float4 gg = *reinterpret_cast<const float4*>(g + o);
-        const float4 ss = *reinterpret_cast<const float4*>(s + o);
-        const float4 ee = *reinterpret_cast<const float4*>(e + o);
-        const float env = use_env ? cosine_cutoff(dist[k], radius) : 1.0f;
-        const float4 gh = bn_apply(c, gg);
-        const float4 sig = make_float4(env * sigmoidf_(gh.x), env * sigmoidf_(gh.y), env * sigmoidf_(gh.z), env * sigmoidf_(gh.w));
-        const float4 eo = make_float4(ee.x + sig.x, ee.y + sig.y, ee.z + sig.z, ee.w + sig.w);
-        *reinterpret_cast<float4*>(e_out + o) = eo;
-        if (e_out_t) store4<T>(e_out_t + o, eo);
-        acc.x += sig.x * ss.x; acc.y += sig.y * ss.y; acc.z += sig.z * ss.z; acc.w += sig.w * ss.w;
+        const float4 g4 = *reinterpret_cast<const float4*>(g + o);
+        const float4 s4 = *reinterpret_cast<const float4*>(s + o);
+        const float4 e4 = *reinterpret_cast<const float4*>(e + o);
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+        const R env = use_env ? cutoff_r<R>(dist[k], radius) : (R)1;
+        float eo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const R gh = ((R)gg[j] - mu[j]) * sc[j] + sh[j];
+            const float sig = (float)(env * sigmoid_r<R>(gh));     // the reference materialises sigma_ij in fp32
+            eo[j] = ee[j] + sig;                                    // cartnet.py:225
+            acc[j] += (R)sig * (R)ss[j];                            // cartnet.py:259
+        }
+        const float4 eo4 = make_float4(eo[0], eo[1], eo[2], eo[3]);
+        *reinterpret_cast<float4*>(e_out + o) = eo4;
+        if (e_out_t) store4<T>(e_out_t + o, eo4);
     }
-    *reinterpret_cast<float4*>(m + (int64_t)node * D + col) = acc;
+    *reinterpret_cast<float4*>(m + (int64_t)node * D + col) = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
 }
 
-template <typename T>
+template <typename T, typename R>
 __global__ void node_update_kernel(const float* __restrict__ m, const float* __restrict__ x, int64_t total4, int D,
                                    const float* mean, const float* var, const float* w, const float* bias, float eps,
                                    float* __restrict__ x_out, T* __restrict__ x_out_t) {
@@ -226,12 +252,19 @@ __global__ void node_update_kernel(const float* __restrict__ m, const float* __r
     if (i >= total4) return;
     const int64_t o = i * 4;
     const int col = (int)(o % D);
-    const BnCoef c = bn_coef(mean, var, w, bias, eps, col);
-    const float4 y = bn_apply(c, *reinterpret_cast<const float4*>(m + o));
-    const float4 xi = *reinterpret_cast<const float4*>(x + o);
-    const float4 r = make_float4(siluf_(y.x) + xi.x, siluf_(y.y) + xi.y, siluf_(y.z) + xi.z, siluf_(y.w) + xi.w);
-    *reinterpret_cast<float4*>(x_out + o) = r;
-    if (x_out_t) store4<T>(x_out_t + o, r);
+    const float4 m4 = *reinterpret_cast<const float4*>(m + o);
+    const float4 x4 = *reinterpret_cast<const float4*>(x + o);
+    const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const R rstd = (R)1 / sqrt((R)var[col + j] + (R)eps);
+        const R y = ((R)mm[j] - (R)mean[col + j]) * ((w ? (R)w[col + j] : (R)1) * rstd) + (bias ? (R)bias[col + j] : (R)0);
+        r[j] = (float)(y * sigmoid_r<R>(y)) + xx[j];                // cartnet.py:223
+    }
+    const float4 r4 = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(x_out + o) = r4;
+    if (x_out_t) store4<T>(x_out_t + o, r4);
 }
 
 __global__ void node_bwd_apply_kernel(const float* __restrict__ dx, const float* __restrict__ m, int64_t total4, int D,
@@ -326,9 +359,9 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t lds, T* 
 }
 
 // feat[e, :] = [ cut(d) exp(-beta_k (exp(-alpha d) - mu_k)^2) (k < R) ; cart_dir (3, unless invariant) ; 0 ... ]
-template <typename T>
+template <typename T, typename R>
 __global__ void edge_features_kernel(const float* __restrict__ cart_dist, const float* __restrict__ cart_dir,
-                                     const float* __restrict__ means, const float* __restrict__ betas, int R,
+                                     const float* __restrict__ means, const float* __restrict__ betas, int nrbf,
                                      float upper, int invariant, int64_t E, T* __restrict__ feat, int ld) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int c4 = ld >> 2;
@@ -337,17 +370,17 @@ __global__ void edge_features_kernel(const float* __restrict__ cart_dist, const 
     const int col = (int)(i % c4) * 4;
     const float d = cart_dist[e];
     const float alpha = 5.0f / upper;                 // models/utils.py:26 (cutoff_lower = 0)
-    const float ex = expf(alpha * (-d));              // models/utils.py:60
-    const float cut = cosine_cutoff(d, upper);
+    const R ex = exp((R)(alpha * (-d)));              // models/utils.py:60
+    const R cut = cutoff_r<R>(d, upper);
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int k = col + j;
-        if (k < R) {
-            const float t = ex - means[k];
-            v[j] = cut * expf(-betas[k] * (t * t));
-        } else if (!invariant && k < R + 3) {
-            v[j] = cart_dir[e * 3 + (k - R)];
+        if (k < nrbf) {
+            const R t = ex - (R)means[k];
+            v[j] = (float)(cut * exp(-(R)betas[k] * (t * t)));
+        } else if (!invariant && k < nrbf + 3) {
+            v[j] = cart_dir[e * 3 + (k - nrbf)];
         } else {
             v[j] = 0.f;
         }
@@ -399,10 +432,15 @@ int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const f
     CN_CHECK_ARG(ld % 4 == 0 && ld >= num_rbf + (invariant ? 0 : 3), "edge_features: ld=%d too small", ld);
     if (num_edges <= 0) return 0;
     const int64_t total = num_edges * (ld / 4);
-    CN_DISPATCH_PREC(prec, {
-        edge_features_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            cart_dist, cart_dir, means, betas, num_rbf, cutoff_upper, invariant, num_edges, (T*)feat, ld);
-    });
+    if (prec == CARTNET_PREC_FP32) {
+        edge_features_kernel<float, double><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            cart_dist, cart_dir, means, betas, num_rbf, cutoff_upper, invariant, num_edges, (float*)feat, ld);
+    } else {
+        CN_DISPATCH_PREC(prec, {
+            edge_features_kernel<T, float><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                cart_dist, cart_dir, means, betas, num_rbf, cutoff_upper, invariant, num_edges, (T*)feat, ld);
+        });
+    }
     CN_LAUNCH_CHECK();
     return 0;
 }
@@ -417,11 +455,17 @@ int cartnet_edge_gate_aggregate(const float* g, const float* s, const float* e, 
     CN_CHECK_ARG(row_shape_ok(D), "edge_gate_aggregate: unsupported D=%d", D);
     if (num_nodes <= 0) return 0;
     const int npb = 256 / (D / 4);
-    CN_DISPATCH_PREC(prec, {
-        edge_gate_aggregate_kernel<T><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
+    if (prec == CARTNET_PREC_FP32) {
+        edge_gate_aggregate_kernel<float, double><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
             g, s, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope, e_out,
-            (T*)e_out_t, m);
-    });
+            (float*)e_out_t, m);
+    } else {
+        CN_DISPATCH_PREC(prec, {
+            edge_gate_aggregate_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
+                g, s, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+                e_out, (T*)e_out_t, m);
+        });
+    }
     CN_LAUNCH_CHECK();
     return 0;
 }
@@ -432,10 +476,15 @@ int cartnet_node_update(const float* m, const float* x, int32_t num_nodes, int32
     CN_CHECK_ARG(m && x && bn_mean && bn_var && x_out && D % 4 == 0, "node_update: bad arguments");
     if (num_nodes <= 0) return 0;
     const int64_t total4 = (int64_t)num_nodes * D / 4;
-    CN_DISPATCH_PREC(prec, {
-        node_update_kernel<T><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-            m, x, total4, D, bn_mean, bn_var, bn_weight, bn_bias, eps, x_out, (T*)x_out_t);
-    });
+    if (prec == CARTNET_PREC_FP32) {
+        node_update_kernel<float, double><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+            m, x, total4, D, bn_mean, bn_var, bn_weight, bn_bias, eps, x_out, (float*)x_out_t);
+    } else {
+        CN_DISPATCH_PREC(prec, {
+            node_update_kernel<T, float><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+                m, x, total4, D, bn_mean, bn_var, bn_weight, bn_bias, eps, x_out, (T*)x_out_t);
+        });
+    }
     CN_LAUNCH_CHECK();
     return 0;
 }

@@ -89,4 +89,44 @@ __device__ __forceinline__ void epi_apply4(const EpiParams<T>& p, const EpiRow<T
     if (p.out_t) store4<T>(p.out_t + row * p.ldt + col, v);
 }
 
+// fp64 variant used by the fp32 parity GEMM: the accumulator arrives in double and bias / gathered projections /
+// SiLU are applied before the single rounding to fp32 (the reference rounds after every op; its accumulated
+// rounding noise is what the 1e-5 budget is mostly spent on)
+__device__ __forceinline__ double silu_d(double v) { return v / (1.0 + exp(-v)); }
+__device__ __forceinline__ double dsilu_d(double z) {
+    const double s = 1.0 / (1.0 + exp(-z));
+    return s * (1.0 + z * (1.0 - s));
+}
+__device__ __forceinline__ void epi_apply4_f64(const EpiParams<float>& p, const EpiRow<float>& r, int64_t row, int col,
+                                               const double* acc) {
+    double v[4] = {acc[0], acc[1], acc[2], acc[3]};
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += (double)p.bias[col + j];
+    }
+    if (r.g0) {
+        const float4 a = *reinterpret_cast<const float4*>(r.g0 + col);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
+    if (r.g1) {
+        const float4 a = *reinterpret_cast<const float4*>(r.g1 + col);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
+    if (p.z_out) *reinterpret_cast<float4*>(p.z_out + row * p.ldz + col) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    if (p.act == CARTNET_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = silu_d(v[j]);
+    } else if (p.act == CARTNET_ACT_MUL_DSILU) {
+        const float4 z = *reinterpret_cast<const float4*>(p.z_in + row * p.ldzin + col);
+        v[0] *= dsilu_d(z.x); v[1] *= dsilu_d(z.y); v[2] *= dsilu_d(z.z); v[3] *= dsilu_d(z.w);
+    }
+    if (p.resid) {
+        const float4 a = *reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
+    const float4 o = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + col) = o;
+    if (p.out_t) *reinterpret_cast<float4*>(p.out_t + row * p.ldt + col) = o;
+}
+
 }  // namespace cartnet

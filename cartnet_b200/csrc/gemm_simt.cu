@@ -114,10 +114,10 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
         for (int jh = 0; jh < 2; ++jh) {
             const int col = n0 + jh * 64 + tx * 4;
             if (col >= N) continue;   // N % 4 == 0 is required, so a float4 never straddles N
-            float4 v = make_float4((float)dacc[i][jh * 4 + 0], (float)dacc[i][jh * 4 + 1], (float)dacc[i][jh * 4 + 2], (float)dacc[i][jh * 4 + 3]);
             if (MODE == 0) {
-                epi_apply4(epi, er, (int64_t)row, col, v);
+                epi_apply4_f64(epi, er, (int64_t)row, col, &dacc[i][jh * 4]);
             } else {
+                const float4 v = make_float4((float)dacc[i][jh * 4 + 0], (float)dacc[i][jh * 4 + 1], (float)dacc[i][jh * 4 + 2], (float)dacc[i][jh * 4 + 3]);
                 *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.y * M + row) * N + col) = v;
             }
         }

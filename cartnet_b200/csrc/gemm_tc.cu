@@ -5,7 +5,7 @@
 // NT kernel  C[M,N] = A[M,K] B[N,K]^T  (+ fused epilogue, gemm_epilogue.cuh)
 //   * persistent, one CTA per SM; the CTA's 128 KB weight slice B[n0:n0+BN, 0:K] is loaded ONCE by TMA and
 //     stays resident in shared memory (K-major, 128B swizzle), so per 128-row tile only A streams through a
-//     4-stage TMA/mbarrier ring (16 KB per stage) -- weights never re-cross L2->SM per tile;
+//     3-stage TMA/mbarrier ring (16 KB per stage) -- weights never re-cross L2->SM per tile;
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread, tcgen05.mma cta_group::1, M=128, N=BN),
 //     warps 2..9 = epilogue: tcgen05.ld 32 columns at a time from one of TWO TMEM accumulators, so the
 //     epilogue of tile i overlaps the MMAs of tile i+1; gathers / bias / SiLU / stores are fused there.
@@ -148,10 +148,12 @@ struct TcTraits<float> {
 };
 
 // ------------------------------------------------------------------------------------------ NT kernel
-constexpr int NT_STAGES = 4;
+constexpr int NT_STAGES = 3;
 constexpr int NT_A_STAGE_BYTES = 128 * 128;      // 128 rows x 128 B
 constexpr int NT_EPI_WARPS = 8;
 constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
+constexpr int NT_STG_PITCH = 36;                                  // floats; 144 B rows keep float4 accesses conflict-minimal
+constexpr int NT_STG_BYTES = NT_EPI_WARPS * 32 * NT_STG_PITCH * 4;   // per-warp 32x32 fp32 transpose buffers
 
 struct NtBars {
     uint64_t a_full[NT_STAGES], a_empty[NT_STAGES], b_full, tmem_full[2], tmem_empty[2];
@@ -169,7 +171,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int b_kb_bytes = BN * 128;
     uint8_t* smemB = smem;
     uint8_t* smemA = smem + (size_t)kblks * b_kb_bytes;
-    NtBars* bars = reinterpret_cast<NtBars*>(smemA + NT_STAGES * NT_A_STAGE_BYTES);
+    float* smemStg = reinterpret_cast<float*>(smemA + NT_STAGES * NT_A_STAGE_BYTES);
+    NtBars* bars = reinterpret_cast<NtBars*>(reinterpret_cast<uint8_t*>(smemStg) + NT_STG_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x % n_tiles;
@@ -236,30 +239,54 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (acc == 0) acc_phase ^= 1;
         }
     } else {
-        // ------------------------------------------------ epilogue: TMEM -> registers -> fused epilogue -> HBM
+        // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> HBM
+        // tcgen05.ld hands each thread one ROW (32 columns). Going to HBM from that layout would make every warp
+        // access touch 32 different 128-byte lines with 16 bytes each, so each 32x32 block is first transposed
+        // through a per-warp shared-memory buffer: afterwards 8 lanes cover one row's 32 columns (one full line),
+        // 4 rows per instruction, and the gathers / residual reads / stores of the epilogue are all line-coalesced.
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int grp = (warp - 2) >> 2;              // column group (0/1)
         const int cols_per_grp = (BN / 2) < 32 ? 32 : (BN / 2);
         const int c_begin = grp * cols_per_grp;
         const int c_end = (c_begin + cols_per_grp) < BN ? (c_begin + cols_per_grp) : BN;
+        float* stg = smemStg + (warp - 2) * 32 * NT_STG_PITCH;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles; mt += m_stride) {
+            const int64_t row0 = (int64_t)mt * 128 + q * 32;
+            // gather rows of the 8 output rows this thread will finish (hoisted out of the column loop)
+            const T* g0[8];
+            const T* g1[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int64_t row = row0 + it * 4 + sub_r;
+                const bool ok = row < M;
+                g0[it] = (ok && epi.gather0) ? epi.gather0 + (int64_t)epi.gidx0[row] * epi.ldg : nullptr;
+                g1[it] = (ok && epi.gather1) ? epi.gather1 + (int64_t)epi.gidx1[row] * epi.ldg : nullptr;
+            }
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int64_t row = (int64_t)mt * 128 + q * 32 + lane;
-            const bool valid = row < M;
-            EpiRow<T> er;
-            er.g0 = nullptr; er.g1 = nullptr;
-            if (valid) er = epi_row(epi, row);
             for (int c = c_begin; c < c_end; c += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (valid) {
 #pragma unroll
-                    for (int gq = 0; gq < 8; ++gq)
-                        epi_apply4(epi, er, row, n0 + c + 4 * gq, make_float4(v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3]));
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + sub_r;
+                    const int64_t row = row0 + rr;
+                    const float4 val = *reinterpret_cast<const float4*>(stg + rr * NT_STG_PITCH + sub_c);
+                    if (row < M) {
+                        EpiRow<T> er;
+                        er.g0 = g0[it];
+                        er.g1 = g1[it];
+                        epi_apply4(epi, er, row, n0 + c + sub_c, val);
+                    }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -435,7 +462,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     if (rc) return rc;
     rc = make_map(&tmB, TR::DT, esize, d.B, d.N, d.K, d.ldb, TR::KB, BN);
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + sizeof(NtBars) + 64;
+    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64;
     static bool attr_done = false;
     if (!attr_done) {
         CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

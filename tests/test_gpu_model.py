@@ -28,13 +28,51 @@ def test_native_library_loaded():
 
 @pytest.mark.parametrize("name", list(common.MODEL_CASES))
 def test_fp32_path_matches_reference_golden(golden_model, name):
-    """north_star: fp32 node features / ADP tensors within 1e-5 relative of the reference layer."""
+    """north_star: ADP tensors / edge features of the whole 4-layer model within 1e-5 relative of the reference,
+    training mode (batch statistics) and eval mode, plus gradients and BatchNorm buffers. Node features after four
+    compounded training-mode layers get 2e-5: on these cases the REFERENCE's own fp32 result is already 8.2e-6
+    away from the exact (fp64) value (BatchNorm over 65 nodes amplifies rounding), so two correct fp32
+    implementations cannot be expected closer than that; the per-layer test above holds 1e-5."""
     shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
     batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes), cholesky=kw["cholesky"],
                                         temperature=kw["temperature"]).to("cuda")
     res = common.run_train_step(_model(kw, seed, lrad, "fp32"), batch0)
-    errs, gerrs = common.check_against_golden(res, golden_model, name, tol=1e-5, gtol=2e-4)
+    errs, gerrs = common.check_against_golden(res, golden_model, name, tol=1e-5, gtol=2e-4, tol_x=2e-5)
     print(name, errs, max(gerrs.values()))
+
+
+@pytest.mark.parametrize("name", list(common.MODEL_CASES))
+@pytest.mark.parametrize("training", [True, False])
+def test_fp32_layer_matches_reference_layer(name, training):
+    """north_star, literally: "fp32 node features ... match the reference PyG LAYER within 1e-5 relative".
+    Every CartNet_layer (and the edge encoder) is fed the oracle's own inputs -- the oracle is bit-identical to
+    the reference's forward (scripts/make_golden.py asserts pred error 0.0) -- and its outputs are compared
+    layer by layer, so rounding differences cannot compound through the four BatchNorm'd layers."""
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
+    batch_cpu = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes), cholesky=kw["cholesky"],
+                                           temperature=kw["temperature"])
+    torch.manual_seed(0)
+    orc = O.OracleCartNet(common.DIM_IN, common.DIM_RBF, common.NUM_LAYERS, layer_radius=lrad, **kw)
+    sd = fixtures.make_state_dict(orc.state_dict(), seed)
+    orc.load_state_dict(sd)
+    model = cartnet_b200.CartNet(common.DIM_IN, common.DIM_RBF, common.NUM_LAYERS, radius=lrad, precision="fp32", **kw)
+    model.load_state_dict(sd)
+    model.cuda()
+    orc.train(training); model.train(training)
+    with torch.no_grad():
+        bo = orc.encoder(batch_cpu.clone())
+        bg = model.encoder(batch_cpu.clone().to("cuda"))
+        assert common.rel_err(bg.edge_attr, bo.edge_attr) < 1e-5 and common.rel_err(bg.x, bo.x) < 1e-5
+        for lo, lg in zip(orc.layers, model.layers):
+            bin_g = batch_cpu.clone().to("cuda")
+            bin_g.x, bin_g.edge_attr = bo.x.clone().cuda(), bo.edge_attr.clone().cuda()     # identical inputs
+            bo = lo(bo)
+            out = lg(bin_g)
+            ex, ee = common.rel_err(out.x, bo.x), common.rel_err(out.edge_attr, bo.edge_attr)
+            assert ex < 1e-5 and ee < 1e-5, (name, training, ex, ee)
+            if training:
+                assert common.rel_err(lg.norm.running_var, lo.norm.running_var) < 1e-5
+                assert common.rel_err(lg.norm2.running_mean, lo.norm2.running_mean) < 1e-5
 
 
 @pytest.mark.parametrize("precision,tol_eval,tol_train", [("bf16", 2e-3, 6e-2), ("tf32", 2e-3, 1e-2)])
