@@ -147,6 +147,58 @@ struct TcTraits<float> {
     static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 };
 
+// ------------------------------------------------------------------------------------------ specialised epilogue
+// The epilogue is the critical path of these GEMMs (K is only 256..1024), so it is specialised at compile time
+// per use-site: EPI is a bit mask of the steps of cartnet_gemm_t that are present; EPI_GENERIC keeps the
+// runtime-checked version for any other combination.
+enum : int { EB_BIAS = 1, EB_GATHER = 2, EB_ZOUT = 4, EB_SILU = 8, EB_DSILU = 16, EB_RESID = 32, EB_OUTF = 64, EB_OUTT = 128 };
+constexpr int EPI_GENERIC = -1;
+
+__device__ __forceinline__ float sigmoid_fast(float v) { return __frcp_rn(1.0f + __expf(-v)); }   // MUFU.EX2 + MUFU.RCP
+__device__ __forceinline__ float silu_fast(float v) { return v * sigmoid_fast(v); }
+__device__ __forceinline__ float dsilu_fast(float z) {
+    const float sg = sigmoid_fast(z);
+    return sg * fmaf(z, 1.0f - sg, 1.0f);
+}
+
+template <int EPI>
+__host__ __device__ constexpr bool epi_has(int bit, bool runtime) { return EPI == EPI_GENERIC ? runtime : ((EPI & bit) != 0); }
+
+// raw (unconverted) 4-element loads so that all global reads of a chunk can be issued before any math / store
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ld_raw4(const T* p);
+template <> __device__ __forceinline__ float4 ld_raw4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ uint2 ld_raw4<__nv_bfloat16>(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 cvt_raw4(const float4& r) { return r; }
+__device__ __forceinline__ float4 cvt_raw4(const uint2& r) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// one float4 (4 consecutive columns) of one output row; inputs were loaded beforehand, outputs point at [row, col]
+template <typename T, int EPI>
+__device__ __forceinline__ void epi_tc4(const EpiParams<T>& p, float4 v, const float4& bias4, bool has_g0, bool has_g1,
+                                        const float4& ga, const float4& gb, const float4& z, const float4& rs, T* z_out,
+                                        float* out_f32, T* out_t) {
+    if (epi_has<EPI>(EB_BIAS, p.bias != nullptr)) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+    if (epi_has<EPI>(EB_GATHER, has_g0)) { v.x += ga.x; v.y += ga.y; v.z += ga.z; v.w += ga.w; }
+    if (epi_has<EPI>(EB_GATHER, has_g1)) { v.x += gb.x; v.y += gb.y; v.z += gb.z; v.w += gb.w; }
+    if (epi_has<EPI>(EB_ZOUT, p.z_out != nullptr)) store4<T>(z_out, v);
+    if (epi_has<EPI>(EB_SILU, p.act == CARTNET_ACT_SILU)) {
+        v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+    }
+    if (epi_has<EPI>(EB_DSILU, p.act == CARTNET_ACT_MUL_DSILU)) {
+        v.x *= dsilu_fast(z.x); v.y *= dsilu_fast(z.y); v.z *= dsilu_fast(z.z); v.w *= dsilu_fast(z.w);
+    }
+    if (epi_has<EPI>(EB_RESID, p.resid != nullptr)) { v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w; }
+    if (epi_has<EPI>(EB_OUTF, p.out_f32 != nullptr)) *reinterpret_cast<float4*>(out_f32) = v;
+    if (epi_has<EPI>(EB_OUTT, p.out_t != nullptr)) store4<T>(out_t, v);
+}
+
 // ------------------------------------------------------------------------------------------ NT kernel
 constexpr int NT_STAGES = 3;
 constexpr int NT_A_STAGE_BYTES = 128 * 128;      // 128 rows x 128 B
@@ -160,7 +212,7 @@ struct NtBars {
     uint32_t tmem_slot;
 };
 
-template <typename T>
+template <typename T, int EPI>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
              int BN, int n_tiles, int m_tiles, EpiParams<T> epi) {
@@ -255,15 +307,15 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles; mt += m_stride) {
             const int64_t row0 = (int64_t)mt * 128 + q * 32;
-            // gather rows of the 8 output rows this thread will finish (hoisted out of the column loop)
-            const T* g0[8];
-            const T* g1[8];
+            // gather-row indices of the 8 output rows this thread finishes (hoisted out of the column loop)
+            int32_t i0[8], i1[8];
+            if (epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr)) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int64_t row = row0 + it * 4 + sub_r;
-                const bool ok = row < M;
-                g0[it] = (ok && epi.gather0) ? epi.gather0 + (int64_t)epi.gidx0[row] * epi.ldg : nullptr;
-                g1[it] = (ok && epi.gather1) ? epi.gather1 + (int64_t)epi.gidx1[row] * epi.ldg : nullptr;
+                for (int it = 0; it < 8; ++it) {
+                    const int64_t row = row0 + it * 4 + sub_r;
+                    i0[it] = row < M ? epi.gidx0[row] : 0;
+                    i1[it] = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
+                }
             }
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -274,19 +326,42 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
+                float4 t4[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) t4[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * NT_STG_PITCH + sub_c);
+                __syncwarp();
+                const int col = n0 + c + sub_c;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) bias4 = *reinterpret_cast<const float4*>(epi.bias + col);
+                const bool has_g0 = epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr);
+                const bool has_g1 = epi_has<EPI>(EB_GATHER, epi.gather1 != nullptr);
+                const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
+                const bool has_r = epi_has<EPI>(EB_RESID, epi.resid != nullptr);
+                // phase 1: every global read of this 32x32 block is issued before any math or store (8..24 loads in
+                // flight per thread), otherwise possible aliasing with the stores would serialise the round trips
+                typename Raw4<T>::type ra[8], rb[8], rz[8];
+                float4 rr[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + sub_r;
-                    const int64_t row = row0 + rr;
-                    const float4 val = *reinterpret_cast<const float4*>(stg + rr * NT_STG_PITCH + sub_c);
+                    const int64_t row = row0 + it * 4 + sub_r;
+                    const bool ok = row < M;
+                    if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                    if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                    if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
+                    if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                }
+                // phase 2: math + stores
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int64_t row = row0 + it * 4 + sub_r;
                     if (row < M) {
-                        EpiRow<T> er;
-                        er.g0 = g0[it];
-                        er.g1 = g1[it];
-                        epi_apply4(epi, er, row, n0 + c + sub_c, val);
+                        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                        epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
+                                        has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
+                                        epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
+                                        epi.out_t + row * epi.ldt + col);
                     }
                 }
-                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -463,13 +538,46 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     rc = make_map(&tmB, TR::DT, esize, d.B, d.N, d.K, d.ldb, TR::KB, BN);
     if (rc) return rc;
     const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+    int mask = 0;
+    if (d.bias) mask |= EB_BIAS;
+    if (d.gather0 && d.gather1) mask |= EB_GATHER;
+    if (d.z_out) mask |= EB_ZOUT;
+    if (d.act == CARTNET_ACT_SILU) mask |= EB_SILU;
+    if (d.act == CARTNET_ACT_MUL_DSILU) mask |= EB_DSILU;
+    if (d.resid) mask |= EB_RESID;
+    if (d.out_f32) mask |= EB_OUTF;
+    if (d.out_t) mask |= EB_OUTT;
+    if ((d.gather0 != nullptr) != (d.gather1 != nullptr)) mask = -2;   // single gather: generic path
+    const EpiParams<T> epi = make_epi<T>(d);
+#define CN_NT_CASE(M_)                                                                                               \
+    if (mask == (M_)) {                                                                                              \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T, (M_)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);   \
+        CN_LAUNCH_CHECK();                                                                                           \
+        return 0;                                                                                                    \
     }
-    tc_nt_kernel<T><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, make_epi<T>(d));
-    CN_LAUNCH_CHECK();
+    CN_NT_CASE(EB_OUTT)                                                   // node projections P
+    CN_NT_CASE(EB_BIAS | EB_GATHER | EB_ZOUT | EB_SILU | EB_OUTT)         // first Linear of both MLPs (per edge)
+    CN_NT_CASE(EB_BIAS | EB_OUTF)                                         // second Linears -> g, s
+    CN_NT_CASE(EB_DSILU | EB_OUTT)                                        // dgrad through the second Linears
+    CN_NT_CASE(EB_RESID | EB_OUTF)                                        // dgrad to e / x with the residual
+    CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTT)                     // edge encoder, first Linear
+    CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF | EB_OUTT)           // edge encoder, second Linear (bf16)
+    CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF)                     // edge encoder, second Linear (tf32)
+#undef CN_NT_CASE
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);
+        CN_LAUNCH_CHECK();
+    }
     return 0;
 }
 
