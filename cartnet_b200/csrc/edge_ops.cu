@@ -41,35 +41,42 @@ __device__ __forceinline__ float4 bn_hat(const BnCoef& c, float4 x) {
 }
 
 // ------------------------------------------------------------------------------------------
-// generic column reduction: F(row, col) -> two float4 contributions (a, b); partial[blk][2][C] fp64
+// generic column reduction: F(row, col) -> NV (2 or 3) float4 contributions; partial[blk][NV][C] fp64
 // ------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partial) {
-    extern __shared__ double sm[];   // [lanes][2][C]
+    constexpr int NV = F::NV;
+    extern __shared__ double sm[];   // [lanes][NV][C]
     const int tpr = C >> 2;                  // threads per row
     const int lanes = 256 / tpr;             // row lanes per block
     const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * 4;
     const int64_t per_block = ceil_div64(rows, gridDim.x);
     const int64_t r0 = blockIdx.x * per_block;
     const int64_t r1 = (r0 + per_block < rows) ? r0 + per_block : rows;
-    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
-        float4 va, vb;
-        f(r, col, va, vb);
-        a[0] += (double)va.x; a[1] += (double)va.y; a[2] += (double)va.z; a[3] += (double)va.w;
-        b[0] += (double)vb.x; b[1] += (double)vb.y; b[2] += (double)vb.z; b[3] += (double)vb.w;
-    }
-    double* mine = sm + (size_t)rl * 2 * C;
+    double acc[NV][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        mine[col + j] = a[j];
-        mine[C + col + j] = b[j];
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[v][j] = 0.0;
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+        float4 val[NV];
+        f(r, col, val);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            acc[v][0] += (double)val[v].x; acc[v][1] += (double)val[v].y; acc[v][2] += (double)val[v].z; acc[v][3] += (double)val[v].w;
+        }
     }
+    double* mine = sm + (size_t)rl * NV * C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[v * C + col + j] = acc[v][j];
     __syncthreads();
-    for (int j = threadIdx.x; j < 2 * C; j += 256) {
+    for (int j = threadIdx.x; j < NV * C; j += 256) {
         double s = 0;
-        for (int l = 0; l < lanes; ++l) s += sm[(size_t)l * 2 * C + j];
-        partial[(size_t)blockIdx.x * 2 * C + j] = s;
+        for (int l = 0; l < lanes; ++l) s += sm[(size_t)l * NV * C + j];
+        partial[(size_t)blockIdx.x * NV * C + j] = s;
     }
 }
 
@@ -77,14 +84,14 @@ enum { FIN_STATS = 0, FIN_SUMS = 1 };
 // FIN_STATS: mean/var (+ running update) from (sum, sumsq); FIN_SUMS: out[0:C]=sum a, out[C:2C]=sum b (ncols_out)
 __global__ void colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, int64_t rows, int mode,
                                        float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ run_mean,
-                                       float* __restrict__ run_var, float momentum, int n_out) {
+                                       float* __restrict__ run_var, float momentum, int n_out, int nv) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (mode == FIN_STATS) {
         if (c >= C) return;
         double s = 0, q = 0;
         for (int b = 0; b < nblocks; ++b) {
-            s += partial[(size_t)b * 2 * C + c];
-            q += partial[(size_t)b * 2 * C + C + c];
+            s += partial[(size_t)b * nv * C + c];
+            q += partial[(size_t)b * nv * C + C + c];
         }
         const double n = (double)rows;
         const double mean = s / n;
@@ -100,7 +107,7 @@ __global__ void colreduce_final_kernel(const double* __restrict__ partial, int n
     } else {
         if (c >= n_out) return;
         double s = 0;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2 * C + c];
+        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nv * C + c];
         out0[c] = (float)s;
     }
 }
@@ -122,36 +129,42 @@ static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, fl
                          float* rv, float momentum, int n_out, cudaStream_t st) {
     const int nb = colreduce_blocks(rows, C);
     const int lanes = 256 / (C / 4);
-    const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
+    const size_t smem = (size_t)lanes * F::NV * C * sizeof(double);
     colreduce_kernel<F><<<nb, 256, smem, st>>>(f, rows, C, partial);
     CN_LAUNCH_CHECK();
     const int nthreads = mode == FIN_STATS ? C : n_out;
     colreduce_final_kernel<<<ceil_div(nthreads, 128), 128, 0, st>>>(partial, nb, C, rows, mode, out0, out1, rm, rv,
-                                                                   momentum, n_out);
+                                                                   momentum, n_out, F::NV);
     CN_LAUNCH_CHECK();
     return 0;
 }
 
 // ---- functors ---------------------------------------------------------------------------
 struct StatsF {
+    static constexpr int NV = 2;
     const float* x; int64_t ld;
-    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
-        a = *reinterpret_cast<const float4*>(x + r * ld + col);
-        b = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
+    __device__ void operator()(int64_t r, int col, float4* o) const {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + col));
+        o[0] = a;
+        o[1] = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
     }
 };
 template <typename TX>
 struct SumF {
+    static constexpr int NV = 2;
     const TX* x; int64_t ld;
-    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
-        a = load4<TX>(x + r * ld + col);
-        b = make_float4(0.f, 0.f, 0.f, 0.f);
+    __device__ void operator()(int64_t r, int col, float4* o) const {
+        o[0] = load4<TX>(x + r * ld + col);
+        o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 };
 struct NodeBwdF {
+    static constexpr int NV = 2;
     const float* dx; const float* m; int D;
     const float *mean, *var, *w, *bias; float eps;
-    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+    __device__ void operator()(int64_t r, int col, float4* o) const {
+        float4& a = o[0];
+        float4& b = o[1];
         BnCoef c = bn_coef(mean, var, w, bias, eps, col);
         float4 mm = *reinterpret_cast<const float4*>(m + r * D + col);
         float4 g = *reinterpret_cast<const float4*>(dx + r * D + col);
@@ -162,22 +175,27 @@ struct NodeBwdF {
 };
 template <typename T>
 struct EdgeBwdF {
+    static constexpr int NV = 3;      // sum dghat | sum dghat*ghat_norm | sum ds  (the last one is d(bias) of MLP_aggr[2])
     const float *g, *s, *dist; const int32_t* dst; const float *de, *dm; int D;
     const float *mean, *var, *w, *bias; float eps, radius; int use_env;
     T* ds_t; float* dghat;
-    __device__ void operator()(int64_t r, int col, float4& a, float4& b) const {
+    __device__ void operator()(int64_t r, int col, float4* out) const {
+        float4& a = out[0];
+        float4& b = out[1];
         BnCoef c = bn_coef(mean, var, w, bias, eps, col);
-        const float env = use_env ? cosine_cutoff(dist[r], radius) : 1.0f;
+        const float env = use_env ? cosine_cutoff(__ldg(dist + r), radius) : 1.0f;
         const int64_t o = r * D + col;
-        float4 gg = *reinterpret_cast<const float4*>(g + o);
-        float4 ss = *reinterpret_cast<const float4*>(s + o);
-        float4 dd = *reinterpret_cast<const float4*>(de + o);
-        float4 dmd = *reinterpret_cast<const float4*>(dm + (int64_t)dst[r] * D + col);
+        // read-only (non-coherent) loads: lets the compiler hoist the loads of the unrolled rows above the stores
+        float4 gg = __ldg(reinterpret_cast<const float4*>(g + o));
+        float4 ss = __ldg(reinterpret_cast<const float4*>(s + o));
+        float4 dd = __ldg(reinterpret_cast<const float4*>(de + o));
+        float4 dmd = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)__ldg(dst + r) * D + col));
         float4 gh = bn_apply(c, gg), hn = bn_hat(c, gg);
         float sg[4] = {sigmoidf_(gh.x), sigmoidf_(gh.y), sigmoidf_(gh.z), sigmoidf_(gh.w)};
         // ds = sig * dm[dst] ; dsig = de_out + s * dm[dst] ; dghat = dsig * env * sg (1 - sg)
         float4 ds = make_float4(env * sg[0] * dmd.x, env * sg[1] * dmd.y, env * sg[2] * dmd.z, env * sg[3] * dmd.w);
         store4<T>(ds_t + o, ds);
+        out[2] = ds;
         a = make_float4((dd.x + ss.x * dmd.x) * env * sg[0] * (1.f - sg[0]), (dd.y + ss.y * dmd.y) * env * sg[1] * (1.f - sg[1]),
                         (dd.z + ss.z * dmd.z) * env * sg[2] * (1.f - sg[2]), (dd.w + ss.w * dmd.w) * env * sg[3] * (1.f - sg[3]));
         *reinterpret_cast<float4*>(dghat + o) = a;
@@ -399,7 +417,7 @@ using namespace cartnet;
 
 extern "C" {
 
-int64_t cartnet_colstats_workspace(int32_t C) { return (int64_t)kRedBlocksMax * 2 * C * (int64_t)sizeof(double); }
+int64_t cartnet_colstats_workspace(int32_t C) { return (int64_t)kRedBlocksMax * 3 * C * (int64_t)sizeof(double); }
 
 int cartnet_colstats(const float* x, int64_t rows, int32_t C, int64_t ld, float* mean, float* var, float* running_mean,
                      float* running_var, float momentum, double* partial, cartnet_stream_t stream) {
@@ -525,7 +543,7 @@ int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* di
     CN_DISPATCH_PREC(prec, {
         EdgeBwdF<T> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
                       (T*)ds_t, dghat};
-        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 2 * D,
+        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D,
                              (cudaStream_t)stream);
     });
     return 0;

@@ -37,15 +37,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: the warp sleeps in hardware (up to ~the hint, in ns) instead of burning
+    // issue slots of the scheduler it shares with the epilogue warps
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -154,7 +156,12 @@ struct TcTraits<float> {
 enum : int { EB_BIAS = 1, EB_GATHER = 2, EB_ZOUT = 4, EB_SILU = 8, EB_DSILU = 16, EB_RESID = 32, EB_OUTF = 64, EB_OUTT = 128 };
 constexpr int EPI_GENERIC = -1;
 
-__device__ __forceinline__ float sigmoid_fast(float v) { return __frcp_rn(1.0f + __expf(-v)); }   // MUFU.EX2 + MUFU.RCP
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // bare MUFU.RCP (1 ulp); __frcp_rn adds a Newton step + slow path
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + __expf(-v)); }   // MUFU.EX2 + MUFU.RCP
 __device__ __forceinline__ float silu_fast(float v) { return v * sigmoid_fast(v); }
 __device__ __forceinline__ float dsilu_fast(float z) {
     const float sg = sigmoid_fast(z);
@@ -338,28 +345,48 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
                 const bool has_r = epi_has<EPI>(EB_RESID, epi.resid != nullptr);
                 // phase 1: every global read of this 32x32 block is issued before any math or store (8..24 loads in
-                // flight per thread), otherwise possible aliasing with the stores would serialise the round trips
+                // flight per thread), otherwise possible aliasing with the stores would serialise the round trips.
+                // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
+                // compiler can interleave the 8 independent rows and hide the MUFU / FMA latencies.
                 typename Raw4<T>::type ra[8], rb[8], rz[8];
                 float4 rr[8];
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + 32 <= (int64_t)M) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int64_t row = row0 + it * 4 + sub_r;
-                    const bool ok = row < M;
-                    if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                    if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                    if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
-                    if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
-                }
-                // phase 2: math + stores
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
+                        if (has_g0) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                        if (has_g1) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                        if (has_z) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
+                        if (has_r) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                    }
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int64_t row = row0 + it * 4 + sub_r;
-                    if (row < M) {
-                        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
                         epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
                                         has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
                                         epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
                                         epi.out_t + row * epi.ldt + col);
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
+                        const bool ok = row < M;
+                        if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                        if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                        if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
+                        if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
+                        if (row < M) {
+                            epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
+                                            has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
+                                            epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
+                                            epi.out_t + row * epi.ldt + col);
+                        }
                     }
                 }
             }

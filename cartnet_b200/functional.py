@@ -160,21 +160,27 @@ class _LayerFn(torch.autograd.Function):
         ops.gemm(prec, ds_t, _to_t(A2.t(), prec), act=ACT_MUL_DSILU, z_in=Z[:, D:], out_t=dZ[:, D:])
         dG2 = ops.gemm_tn(prec, dg_t, H[:, :D])
         dA2 = ops.gemm_tn(prec, ds_t, H[:, D:])
-        dbg2 = ops.colsum(dg_t, prec)
-        dba2 = ops.colsum(ds_t, prec)
+        # bias gradients without extra passes over [E, D]: d(ba2) = sum_e ds is a third output of the reduction
+        # above; d(bg2) = sum_e dg is identically zero under batch statistics (BatchNorm removes any shift of g;
+        # the reference's value is pure rounding noise) and gamma*rstd*sum_e dghat under running statistics
+        dba2 = sums1[2 * D:].clone()
+        if training:
+            dbg2 = torch.zeros(D, dtype=torch.float32, device=dev)
+        else:
+            dbg2 = w1.detach() * torch.rsqrt(var1 + ops.EPS_BN) * sums1[:D]
         # first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
         de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
         ops.gemm(prec, dZ, _to_t(W1e.t(), prec), resid=de_out, out_f32=de_in)
         dW1e = ops.gemm_tn(prec, dZ, e_t)
-        db1 = ops.colsum(dZ, prec)
         # first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
         dP = torch.empty(N, 4 * D, dtype=T, device=dev)
         ops.segment_sum(dZ, plan.row_ptr, None, N, dP[:, :2 * D], prec)
         ops.segment_sum(dZ, plan.col_ptr, plan.perm_src, N, dP[:, 2 * D:], prec)
+        db1 = ops.colsum(dP[:, :2 * D], prec)        # sum_e dZ = sum_n (sum_{e -> n} dZ): N rows instead of E
         dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
         ops.gemm(prec, dP, _to_t(W1n.t(), prec), resid=dx_out, out_f32=dx_in)
         dW1n = ops.gemm_tn(prec, dP, x_t)
-        dw1, db1n = sums1[D:].clone(), sums1[:D].clone()
+        dw1, db1n = sums1[D:2 * D].clone(), sums1[:D].clone()
         dw2, db2n = sums2[D:].clone(), sums2[:D].clone()
         return dx_in, de_in, dW1n, dW1e, db1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n, None
 

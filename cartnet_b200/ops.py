@@ -322,7 +322,8 @@ def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training: bool):
 
 def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, radius: float, use_envelope: bool,
                   training: bool, prec: int):
-    """Returns ds_t, dg_t (T, [E,D]) and sums [2D] (d bias | d weight of the edge BatchNorm)."""
+    """Returns ds_t, dg_t (T, [E,D]) and sums [3D]: sum dghat (= d bias of the edge BatchNorm) | sum dghat*ghat_norm
+    (= d weight) | sum ds (= d bias of MLP_aggr[2])."""
     lib = _lib.load()
     de_out = _req(de_out.contiguous(), torch.float32, "de_out")
     E, D = int(g.shape[0]), int(g.shape[1])
@@ -330,7 +331,7 @@ def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, ra
     ds_t = torch.empty(E, D, dtype=T, device=g.device)
     dg_t = torch.empty(E, D, dtype=T, device=g.device)
     dghat = torch.empty(E, D, dtype=torch.float32, device=g.device)
-    sums = torch.empty(2 * D, dtype=torch.float32, device=g.device)
+    sums = torch.empty(3 * D, dtype=torch.float32, device=g.device)
     part = _partial(g.device, int(lib.cartnet_colstats_workspace(D)))
     st = _stream()
     _lib.check(lib.cartnet_edge_gate_bwd_reduce(

@@ -198,7 +198,7 @@ int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t n
 
 /* Backward edge pass, step 1 (per edge, channel):  dmd = dm[dst];  ds = sig * dmd  -> ds_t (T);
  * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat (fp32);
- * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm. */
+ * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm, sums[2D:3D] = sum_e ds (sums has 3D entries). */
 int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
                                  const float* bn_mean, const float* bn_var, const float* bn_weight,

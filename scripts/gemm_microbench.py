@@ -69,3 +69,5 @@ if which in ("all", "tn"):
     tn(E, 512, 256)
 if which == "one":
     nt(E, 256, 256, "tout")
+if which == "gs":
+    nt(E, 512, 256, "gather_silu")

@@ -159,7 +159,7 @@ def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, ra
     corr = (s1 / n + gn * s2 / n) if training else 0.0
     dg = _f(bn_w) * rstd * (dghat - corr)
     T = t_dtype(prec)
-    return ds.to(T), dg.to(T), torch.cat([s1, s2]).float()
+    return ds.to(T), dg.to(T), torch.cat([s1, s2, ds.sum(0)]).float()
 
 
 def segment_sum(x, ptr, perm, num_nodes, out, prec):
