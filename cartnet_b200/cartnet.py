@@ -69,6 +69,24 @@ def get_plan(batch) -> ops.GraphPlan:
     return plan
 
 
+_mask_cache: "OrderedDict[int, tuple]" = OrderedDict()
+
+
+def _mask_index(mask: torch.Tensor) -> torch.Tensor:
+    """Row indices of a boolean mask, computed once per mask tensor (identity-keyed like the plan cache).
+    `x[mask]` would force a device->host sync on every step (the result size is data dependent); with the
+    indices cached the training step has no host synchronisation at all."""
+    ent = _mask_cache.get(id(mask))
+    if ent is not None and ent[0] is mask and ent[2] == mask._version:
+        _mask_cache.move_to_end(id(mask))
+        return ent[1]
+    idx = torch.nonzero(mask, as_tuple=False).squeeze(-1)
+    _mask_cache[id(mask)] = (mask, idx, mask._version)
+    while len(_mask_cache) > 8:
+        _mask_cache.popitem(last=False)
+    return idx
+
+
 def _operand(t: torch.Tensor, prec: int):
     """T-typed copy left on the tensor by the producing kernel, if it is still valid."""
     sh = getattr(t, "_cn_t", None)
@@ -238,7 +256,7 @@ class Cholesky_head(nn.Module):
         self.MLP = nn.Sequential(nn.Linear(dim_in, dim_in // 2), nn.SiLU(inplace=True), nn.Linear(dim_in // 2, 6))
 
     def forward(self, batch):
-        pred = self.MLP(batch.x[batch.non_H_mask])
+        pred = self.MLP(batch.x.index_select(0, _mask_index(batch.non_H_mask)))     # == batch.x[batch.non_H_mask]
         diag = F.softplus(pred[:, :3])
         L = torch.zeros(pred.size(0), 3, 3, device=pred.device, dtype=pred.dtype)
         L[:, [0, 1, 2], [0, 1, 2]] = diag

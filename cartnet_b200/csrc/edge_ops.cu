@@ -46,22 +46,57 @@ __device__ __forceinline__ float4 bn_hat(const BnCoef& c, float4 x) {
 template <class F>
 __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, double* __restrict__ partial) {
     constexpr int NV = F::NV;
-    extern __shared__ double sm[];   // [lanes][NV][C]
+    constexpr int U = 4;                     // rows per inner batch: loads of all U rows are issued together
+    extern __shared__ double sm[];           // [lanes][NV][C]
     const int tpr = C >> 2;                  // threads per row
     const int lanes = 256 / tpr;             // row lanes per block
     const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * 4;
     const int64_t per_block = ceil_div64(rows, gridDim.x);
     const int64_t r0 = blockIdx.x * per_block;
     const int64_t r1 = (r0 + per_block < rows) ? r0 + per_block : rows;
+    const typename F::State st = f.init(col);   // per-column constants (BatchNorm coefficients) hoisted out of the row loop
     double acc[NV][4];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[v][j] = 0.0;
-#pragma unroll 4
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+    int64_t r = r0 + rl;
+    for (; r + (int64_t)(U - 1) * lanes < r1; r += (int64_t)U * lanes) {
+        typename F::In in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) f.load(r + (int64_t)u * lanes, col, in[u]);
+        if (F::F32_PARTIAL) {                // U values are summed in fp32 (fixed order), the running total stays in fp64
+            float4 part[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) part[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float4 val[NV];
+                f.compute(st, r + (int64_t)u * lanes, col, in[u], val);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) { part[v].x += val[v].x; part[v].y += val[v].y; part[v].z += val[v].z; part[v].w += val[v].w; }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[v][0] += (double)part[v].x; acc[v][1] += (double)part[v].y; acc[v][2] += (double)part[v].z; acc[v][3] += (double)part[v].w;
+            }
+        } else {                             // BatchNorm statistics: every term goes straight into fp64 (E[x^2]-E[x]^2 cancels)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float4 val[NV];
+                f.compute(st, r + (int64_t)u * lanes, col, in[u], val);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    acc[v][0] += (double)val[v].x; acc[v][1] += (double)val[v].y; acc[v][2] += (double)val[v].z; acc[v][3] += (double)val[v].w;
+                }
+            }
+        }
+    }
+    for (; r < r1; r += lanes) {
+        typename F::In in;
+        f.load(r, col, in);
         float4 val[NV];
-        f(r, col, val);
+        f.compute(st, r, col, in, val);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             acc[v][0] += (double)val[v].x; acc[v][1] += (double)val[v].y; acc[v][2] += (double)val[v].z; acc[v][3] += (double)val[v].w;
@@ -139,67 +174,96 @@ static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, fl
     return 0;
 }
 
-// ---- functors ---------------------------------------------------------------------------
+// ---- functors: init(col) -> State ; load(row, col, In&) ; compute(State, row, col, In, float4 out[NV]) --------
+struct NoState {};
 struct StatsF {
     static constexpr int NV = 2;
+    static constexpr bool F32_PARTIAL = false;
+    using State = NoState;
+    using In = float4;
     const float* x; int64_t ld;
-    __device__ void operator()(int64_t r, int col, float4* o) const {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + col));
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(int64_t r, int col, In& in) const { in = __ldg(reinterpret_cast<const float4*>(x + r * ld + col)); }
+    __device__ void compute(const State&, int64_t, int, const In& a, float4* o) const {
         o[0] = a;
         o[1] = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
     }
 };
 template <typename TX>
 struct SumF {
-    static constexpr int NV = 2;
+    static constexpr int NV = 1;
+    static constexpr bool F32_PARTIAL = true;
+    using State = NoState;
+    using In = float4;
     const TX* x; int64_t ld;
-    __device__ void operator()(int64_t r, int col, float4* o) const {
-        o[0] = load4<TX>(x + r * ld + col);
-        o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(int64_t r, int col, In& in) const { in = load4<TX>(x + r * ld + col); }
+    __device__ void compute(const State&, int64_t, int, const In& a, float4* o) const { o[0] = a; }
 };
 struct NodeBwdF {
     static constexpr int NV = 2;
+    static constexpr bool F32_PARTIAL = false;
+    using State = BnCoef;
+    struct In { float4 m, g; };
     const float* dx; const float* m; int D;
     const float *mean, *var, *w, *bias; float eps;
-    __device__ void operator()(int64_t r, int col, float4* o) const {
-        float4& a = o[0];
-        float4& b = o[1];
-        BnCoef c = bn_coef(mean, var, w, bias, eps, col);
-        float4 mm = *reinterpret_cast<const float4*>(m + r * D + col);
-        float4 g = *reinterpret_cast<const float4*>(dx + r * D + col);
-        float4 y = bn_apply(c, mm), h = bn_hat(c, mm);
-        a = make_float4(g.x * dsiluf_(y.x), g.y * dsiluf_(y.y), g.z * dsiluf_(y.z), g.w * dsiluf_(y.w));
-        b = make_float4(a.x * h.x, a.y * h.y, a.z * h.z, a.w * h.w);
+    __device__ State init(int col) const { return bn_coef(mean, var, w, bias, eps, col); }
+    __device__ void load(int64_t r, int col, In& in) const {
+        in.m = __ldg(reinterpret_cast<const float4*>(m + r * D + col));
+        in.g = __ldg(reinterpret_cast<const float4*>(dx + r * D + col));
+    }
+    __device__ void compute(const State& c, int64_t, int, const In& in, float4* o) const {
+        const float4 y = bn_apply(c, in.m), h = bn_hat(c, in.m);
+        const float4 a = make_float4(in.g.x * dsiluf_(y.x), in.g.y * dsiluf_(y.y), in.g.z * dsiluf_(y.z), in.g.w * dsiluf_(y.w));
+        o[0] = a;
+        o[1] = make_float4(a.x * h.x, a.y * h.y, a.z * h.z, a.w * h.w);
     }
 };
-template <typename T>
+// FAST: MUFU-based sigmoid / cosine for the tensor-core modes (their operands carry >= 2^-11 rounding anyway);
+// the fp32 parity mode keeps expf / cosf / IEEE division.
+template <bool FAST> __device__ __forceinline__ float sigmoid_sel(float v) {
+    if (FAST) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + __expf(-v))); return r; }
+    return sigmoidf_(v);
+}
+template <bool FAST> __device__ __forceinline__ float cutoff_sel(float d, float upper) {
+    if (FAST) return d < upper ? 0.5f * (__cosf(d * 3.14159265358979323846f / upper) + 1.0f) : 0.0f;
+    return cosine_cutoff(d, upper);
+}
+template <typename T, bool FAST>
 struct EdgeBwdF {
     static constexpr int NV = 3;      // sum dghat | sum dghat*ghat_norm | sum ds  (the last one is d(bias) of MLP_aggr[2])
+    static constexpr bool F32_PARTIAL = true;
+    using State = BnCoef;
+    struct In { float4 g, s, de, dmd; float dist; };
     const float *g, *s, *dist; const int32_t* dst; const float *de, *dm; int D;
     const float *mean, *var, *w, *bias; float eps, radius; int use_env;
     T* ds_t; float* dghat;
-    __device__ void operator()(int64_t r, int col, float4* out) const {
-        float4& a = out[0];
-        float4& b = out[1];
-        BnCoef c = bn_coef(mean, var, w, bias, eps, col);
-        const float env = use_env ? cosine_cutoff(__ldg(dist + r), radius) : 1.0f;
+    __device__ State init(int col) const { return bn_coef(mean, var, w, bias, eps, col); }
+    __device__ void load(int64_t r, int col, In& in) const {
+        // read-only (non-coherent) loads of U rows are all in flight before the first store
         const int64_t o = r * D + col;
-        // read-only (non-coherent) loads: lets the compiler hoist the loads of the unrolled rows above the stores
-        float4 gg = __ldg(reinterpret_cast<const float4*>(g + o));
-        float4 ss = __ldg(reinterpret_cast<const float4*>(s + o));
-        float4 dd = __ldg(reinterpret_cast<const float4*>(de + o));
-        float4 dmd = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)__ldg(dst + r) * D + col));
-        float4 gh = bn_apply(c, gg), hn = bn_hat(c, gg);
-        float sg[4] = {sigmoidf_(gh.x), sigmoidf_(gh.y), sigmoidf_(gh.z), sigmoidf_(gh.w)};
+        in.g = __ldg(reinterpret_cast<const float4*>(g + o));
+        in.s = __ldg(reinterpret_cast<const float4*>(s + o));
+        in.de = __ldg(reinterpret_cast<const float4*>(de + o));
+        in.dmd = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)__ldg(dst + r) * D + col));
+        in.dist = use_env ? __ldg(dist + r) : 0.f;
+    }
+    __device__ void compute(const State& c, int64_t r, int col, const In& in, float4* out) const {
+        const float env = use_env ? cutoff_sel<FAST>(in.dist, radius) : 1.0f;
+        const int64_t o = r * D + col;
+        const float4 gh = bn_apply(c, in.g), hn = bn_hat(c, in.g);
+        const float sg[4] = {sigmoid_sel<FAST>(gh.x), sigmoid_sel<FAST>(gh.y), sigmoid_sel<FAST>(gh.z), sigmoid_sel<FAST>(gh.w)};
         // ds = sig * dm[dst] ; dsig = de_out + s * dm[dst] ; dghat = dsig * env * sg (1 - sg)
-        float4 ds = make_float4(env * sg[0] * dmd.x, env * sg[1] * dmd.y, env * sg[2] * dmd.z, env * sg[3] * dmd.w);
+        const float4 ds = make_float4(env * sg[0] * in.dmd.x, env * sg[1] * in.dmd.y, env * sg[2] * in.dmd.z, env * sg[3] * in.dmd.w);
         store4<T>(ds_t + o, ds);
-        out[2] = ds;
-        a = make_float4((dd.x + ss.x * dmd.x) * env * sg[0] * (1.f - sg[0]), (dd.y + ss.y * dmd.y) * env * sg[1] * (1.f - sg[1]),
-                        (dd.z + ss.z * dmd.z) * env * sg[2] * (1.f - sg[2]), (dd.w + ss.w * dmd.w) * env * sg[3] * (1.f - sg[3]));
+        const float4 a = make_float4((in.de.x + in.s.x * in.dmd.x) * env * sg[0] * (1.f - sg[0]),
+                                     (in.de.y + in.s.y * in.dmd.y) * env * sg[1] * (1.f - sg[1]),
+                                     (in.de.z + in.s.z * in.dmd.z) * env * sg[2] * (1.f - sg[2]),
+                                     (in.de.w + in.s.w * in.dmd.w) * env * sg[3] * (1.f - sg[3]));
         *reinterpret_cast<float4*>(dghat + o) = a;
-        b = make_float4(a.x * hn.x, a.y * hn.y, a.z * hn.z, a.w * hn.w);
+        out[0] = a;
+        out[1] = make_float4(a.x * hn.x, a.y * hn.y, a.z * hn.z, a.w * hn.w);
+        out[2] = ds;
     }
 };
 
@@ -540,11 +604,16 @@ int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* di
     CN_CHECK_ARG(g && s && dist && dst32 && de_out && dm && bn_mean && bn_var && ds_t && dghat && sums && partial &&
                      num_edges > 0, "edge_gate_bwd_reduce: bad arguments");
     CN_CHECK_ARG(colreduce_shape_ok(D), "edge_gate_bwd_reduce: unsupported D=%d", D);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prec == CARTNET_PREC_FP32) {
+        EdgeBwdF<float, false> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+                                 (float*)ds_t, dghat};
+        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
+    }
     CN_DISPATCH_PREC(prec, {
-        EdgeBwdF<T> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-                      (T*)ds_t, dghat};
-        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D,
-                             (cudaStream_t)stream);
+        EdgeBwdF<T, true> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+                            (T*)ds_t, dghat};
+        return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
     });
     return 0;
 }
