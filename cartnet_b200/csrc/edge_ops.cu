@@ -116,18 +116,27 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
 }
 
 enum { FIN_STATS = 0, FIN_SUMS = 1 };
-// FIN_STATS: mean/var (+ running update) from (sum, sumsq); FIN_SUMS: out[0:C]=sum a, out[C:2C]=sum b (ncols_out)
-__global__ void colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, int64_t rows, int mode,
-                                       float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ run_mean,
-                                       float* __restrict__ run_var, float momentum, int n_out, int nv) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Sum of partial[b][j] over blocks b, one WARP per column j: lane l adds blocks l, l+32, ... in order, then a
+// fixed-shape butterfly -- deterministic, and 32x less serial latency than one thread walking all blocks.
+__device__ __forceinline__ double warp_block_sum(const double* __restrict__ partial, int nblocks, int stride, int j, int lane) {
+    double s = 0;
+    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * stride + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+// FIN_STATS: mean/var (+ running update) from (sum, sumsq); FIN_SUMS: out0[j] = sum of value j (j < n_out)
+__global__ void __launch_bounds__(256)
+colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, int64_t rows, int mode,
+                       float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ run_mean,
+                       float* __restrict__ run_var, float momentum, int n_out, int nv) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per output column
     if (mode == FIN_STATS) {
         if (c >= C) return;
-        double s = 0, q = 0;
-        for (int b = 0; b < nblocks; ++b) {
-            s += partial[(size_t)b * nv * C + c];
-            q += partial[(size_t)b * nv * C + C + c];
-        }
+        const double s = warp_block_sum(partial, nblocks, nv * C, c, lane);
+        const double q = warp_block_sum(partial, nblocks, nv * C, C + c, lane);
+        if (lane != 0) return;
         const double n = (double)rows;
         const double mean = s / n;
         double var = q / n - mean * mean;
@@ -141,9 +150,8 @@ __global__ void colreduce_final_kernel(const double* __restrict__ partial, int n
         }
     } else {
         if (c >= n_out) return;
-        double s = 0;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nv * C + c];
-        out0[c] = (float)s;
+        const double s = warp_block_sum(partial, nblocks, nv * C, c, lane);
+        if (lane == 0) out0[c] = (float)s;
     }
 }
 
@@ -168,8 +176,8 @@ static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, fl
     colreduce_kernel<F><<<nb, 256, smem, st>>>(f, rows, C, partial);
     CN_LAUNCH_CHECK();
     const int nthreads = mode == FIN_STATS ? C : n_out;
-    colreduce_final_kernel<<<ceil_div(nthreads, 128), 128, 0, st>>>(partial, nb, C, rows, mode, out0, out1, rm, rv,
-                                                                   momentum, n_out, F::NV);
+    colreduce_final_kernel<<<ceil_div(nthreads, 8), 256, 0, st>>>(partial, nb, C, rows, mode, out0, out1, rm, rv,
+                                                                 momentum, n_out, F::NV);
     CN_LAUNCH_CHECK();
     return 0;
 }
