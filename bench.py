@@ -68,7 +68,11 @@ def make_host_batch(batch: int, seed: int, device):
     h = host_structures(batch, seed)
     gr = build_graph(h["pos"].to(device), h["cell"].to(device), h["natoms"].to(device), 5.0)
     h["edge_index"], h["cart_dist"], h["cart_dir"] = gr["edge_index"].cpu(), gr["cart_dist"].cpu(), gr["cart_dir"].cpu()
-    return CrystalBatch(**h).pin_memory()
+    # facts the data pipeline knows statically: radius_graph_pbc output is dst-sorted; the non-H atom list is fixed
+    h["non_H_index"] = torch.nonzero(h["non_H_mask"]).squeeze(-1)
+    b = CrystalBatch(**h).pin_memory()
+    b.edges_dst_sorted = True
+    return b
 
 
 def shallow(b):

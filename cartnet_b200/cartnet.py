@@ -62,7 +62,7 @@ def get_plan(batch) -> ops.GraphPlan:
     if ent is not None and ent[0] is ei and ent[1].num_nodes == n and ent[2] == ei._version:
         _plan_cache.move_to_end(id(ei))
         return ent[1]
-    plan = ops.graph_plan(ei, n)
+    plan = ops.graph_plan(ei, n, assume_dst_sorted=bool(getattr(batch, "edges_dst_sorted", False)))
     _plan_cache[id(ei)] = (ei, plan, ei._version)
     while len(_plan_cache) > 4:
         _plan_cache.popitem(last=False)
@@ -99,6 +99,25 @@ def _tag(t: torch.Tensor, t_copy, prec: int):
     if t_copy is not None:
         t._cn_t = (t_copy, prec, t._version)
     return t
+
+
+class _PackW1(torch.autograd.Function):
+    """[G1 | A1] ([D,3D] each, columns [x_i | x_j | e]) -> W1n [4D,D] = [G1_i;A1_i;G1_j;A1_j], W1e [2D,D] = [G1_e;A1_e].
+    One Function instead of a dozen slice/cat autograd nodes: the backward is two concatenations."""
+
+    @staticmethod
+    def forward(ctx, G1, A1):
+        D = G1.shape[0]
+        W1n = torch.cat([G1[:, :D], A1[:, :D], G1[:, D:2 * D], A1[:, D:2 * D]], dim=0)
+        W1e = torch.cat([G1[:, 2 * D:], A1[:, 2 * D:]], dim=0)
+        return W1n, W1e
+
+    @staticmethod
+    def backward(ctx, dW1n, dW1e):
+        D = dW1e.shape[1]
+        dG1 = torch.cat([dW1n[:D], dW1n[2 * D:3 * D], dW1e[:D]], dim=1)
+        dA1 = torch.cat([dW1n[D:2 * D], dW1n[3 * D:], dW1e[D:]], dim=1)
+        return dG1, dA1
 
 
 class _PrecisionMixin:
@@ -204,10 +223,7 @@ class CartNet_layer(nn.Module, _PrecisionMixin):
         self.radius = float(_cfg_get("radius", 5.0 if radius is None else radius))   # cartnet.py:201
 
     def _packed(self):
-        D = self.dim_in
-        G1, A1 = self.MLP_gate[0].weight, self.MLP_aggr[0].weight        # [D, 3D], columns [x_i | x_j | e]
-        W1n = torch.cat([G1[:, :D], A1[:, :D], G1[:, D:2 * D], A1[:, D:2 * D]], dim=0)
-        W1e = torch.cat([G1[:, 2 * D:], A1[:, 2 * D:]], dim=0)
+        W1n, W1e = _PackW1.apply(self.MLP_gate[0].weight, self.MLP_aggr[0].weight)     # [D, 3D], columns [x_i | x_j | e]
         b1 = torch.cat([self.MLP_gate[0].bias, self.MLP_aggr[0].bias])
         return (W1n, W1e, b1, self.MLP_gate[2].weight, self.MLP_aggr[2].weight, self.MLP_gate[2].bias,
                 self.MLP_aggr[2].bias, self.norm.weight, self.norm.bias, self.norm2.weight, self.norm2.bias)
@@ -256,7 +272,10 @@ class Cholesky_head(nn.Module):
         self.MLP = nn.Sequential(nn.Linear(dim_in, dim_in // 2), nn.SiLU(inplace=True), nn.Linear(dim_in // 2, 6))
 
     def forward(self, batch):
-        pred = self.MLP(batch.x.index_select(0, _mask_index(batch.non_H_mask)))     # == batch.x[batch.non_H_mask]
+        idx = getattr(batch, "non_H_index", None)        # optional precomputed nonzero(non_H_mask) from the data pipeline
+        if idx is None:
+            idx = _mask_index(batch.non_H_mask)
+        pred = self.MLP(batch.x.index_select(0, idx))                                # == batch.x[batch.non_H_mask]
         diag = F.softplus(pred[:, :3])
         L = torch.zeros(pred.size(0), 3, 3, device=pred.device, dtype=pred.dtype)
         L[:, [0, 1, 2], [0, 1, 2]] = diag

@@ -144,7 +144,10 @@ class GraphPlan:
     key: tuple = ()
 
 
-def graph_plan(edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
+def graph_plan(edge_index: torch.Tensor, num_nodes: int, assume_dst_sorted: bool = False) -> GraphPlan:
+    """assume_dst_sorted=True (a promise of the data pipeline: every graph produced by radius_graph_pbc is
+    dst-sorted with in-range indices, SURVEY.md §4 property 3) skips the one device->host read of the check flags,
+    so building the plan does not synchronise the stream."""
     lib = _lib.load()
     edge_index = _req(edge_index.contiguous(), torch.int64, "edge_index")
     dev = edge_index.device
@@ -154,7 +157,7 @@ def graph_plan(edge_index: torch.Tensor, num_nodes: int) -> GraphPlan:
     dst32 = torch.empty(E, dtype=torch.int32, device=dev)
     flags = torch.empty(2, dtype=torch.int32, device=dev)
     _lib.check(lib.cartnet_graph_split(_p(edge_index), E, num_nodes, _p(src32), _p(dst32), _p(flags), st), "graph_split")
-    unsorted, oob = (int(v) for v in flags.tolist())        # host sync, once per batch
+    unsorted, oob = (0, 0) if assume_dst_sorted else (int(v) for v in flags.tolist())   # host sync, once per batch
     if oob:
         raise IndexError("cartnet_b200: edge_index has entries outside [0, %d)" % num_nodes)
     cursor = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)

@@ -44,7 +44,7 @@ def _bn(x, mean, var, w, b):
     return xhat * w + b, xhat, rstd
 
 
-def graph_plan(edge_index, num_nodes):
+def graph_plan(edge_index, num_nodes, assume_dst_sorted=False):
     E = edge_index.shape[1]
     src, dst = edge_index[0], edge_index[1]
     if ((src < 0) | (src >= num_nodes) | (dst < 0) | (dst >= num_nodes)).any():
