@@ -230,7 +230,7 @@ struct NodeBwdF {
 // FAST: MUFU-based sigmoid / cosine for the tensor-core modes (their operands carry >= 2^-11 rounding anyway);
 // the fp32 parity mode keeps expf / cosf / IEEE division.
 template <bool FAST> __device__ __forceinline__ float sigmoid_sel(float v) {
-    if (FAST) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + __expf(-v))); return r; }
+    if (FAST) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v)); return fmaf(0.5f, t, 0.5f); }   // one MUFU op
     return sigmoidf_(v);
 }
 template <bool FAST> __device__ __forceinline__ float cutoff_sel(float d, float upper) {

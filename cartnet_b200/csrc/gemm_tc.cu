@@ -156,16 +156,20 @@ struct TcTraits<float> {
 enum : int { EB_BIAS = 1, EB_GATHER = 2, EB_ZOUT = 4, EB_SILU = 8, EB_DSILU = 16, EB_RESID = 32, EB_OUTF = 64, EB_OUTT = 128 };
 constexpr int EPI_GENERIC = -1;
 
-__device__ __forceinline__ float rcp_approx(float x) {
+// sigmoid(v) = 0.5 tanh(v/2) + 0.5: ONE MUFU op (tanh.approx, ~2^-11 rel. error -- below the bf16 / tf32 operand
+// rounding of these modes) instead of EX2 + RCP; MUFU is quarter-rate and was ~25% of the first Linear's epilogue.
+__device__ __forceinline__ float tanh_approx(float x) {
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // bare MUFU.RCP (1 ulp); __frcp_rn adds a Newton step + slow path
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + __expf(-v)); }   // MUFU.EX2 + MUFU.RCP
-__device__ __forceinline__ float silu_fast(float v) { return v * sigmoid_fast(v); }
+__device__ __forceinline__ float silu_fast(float v) {
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_approx(h), h);                      // v * sigmoid(v)
+}
 __device__ __forceinline__ float dsilu_fast(float z) {
-    const float sg = sigmoid_fast(z);
-    return sg * fmaf(z, 1.0f - sg, 1.0f);
+    const float sg = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+    return sg * fmaf(z, 1.0f - sg, 1.0f);                   // s (1 + z (1 - s))
 }
 
 template <int EPI>
