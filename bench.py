@@ -320,12 +320,16 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host batch -> .to(device) -> model -> loss.item()
     h2d = int(np.mean([batch_bytes(b) for b in host_batches]))
 
-    def e2e_step(i):
-        b = shallow(host_batches[i % nb]).to(dev, non_blocking=True)
-        loss = step(b)
-        return float(loss.item())            # device -> host read of the step's result
+    from cartnet_b200 import DevicePrefetcher
+    n_e2e_warm = max(2, args.warmup // 2)
+    feed = DevicePrefetcher((host_batches[i % nb] for i in range(n_e2e_warm + args.steps)), dev)
 
-    for i in range(max(2, args.warmup // 2)):
+    def e2e_step(i):
+        b = next(feed)                       # pinned host batch -> device (copy + graph plan issued one step ahead)
+        loss = step(b)
+        return float(loss.item())            # device -> host read of the step's result, every step
+
+    for i in range(n_e2e_warm):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * graphs_step / (ms_e2e * 1e-3)
@@ -338,6 +342,8 @@ def run_ours(args):
 
     # ---- roofline attribution (extra instrumented pass, not part of any reported time)
     pk = peaks()
+    from cartnet_b200 import functional as CF
+    CF.USE_NATIVE_LAYER = False              # same kernels, issued one by one from Python so that each can be timed
     with OpTimer() as ot:
         for i in range(2):
             step(shallow(dev_batches[i % nb]), collective=False)     # rank 0 only: no collective in this pass

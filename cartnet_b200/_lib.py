@@ -34,6 +34,21 @@ class GemmDesc(C.Structure):
     ]
 
 
+class LayerDesc(C.Structure):
+    """Mirror of `cartnet_layer_t` (field order must match include/cartnet_b200.h)."""
+    _PTRS1 = ["src32", "dst32", "row_ptr", "col_ptr", "perm_src", "dist", "x", "e", "x_t", "e_t",
+              "G1", "A1", "bg1", "ba1", "G2", "A2", "bg2", "ba2", "bn1_w", "bn1_b", "bn2_w", "bn2_b",
+              "bn1_rm", "bn1_rv", "bn2_rm", "bn2_rv",
+              "W1n_t", "W1e_t", "G2_t", "A2_t", "W1nT_t", "W1eT_t", "G2T_t", "A2T_t", "b1",
+              "P", "Z", "H", "g", "s", "m", "mean1", "var1", "mean2", "var2", "x_out", "e_out", "x_out_t", "e_out_t",
+              "dx_out", "de_out", "dm", "ds_t", "dg_t", "dghat", "dZ", "dP", "sums1", "sums2", "dx_in", "de_in",
+              "dG1", "dA1", "dbg1", "dba1", "dG2", "dA2", "dbg2", "dba2", "dbn1_w", "dbn1_b", "dbn2_w", "dbn2_b",
+              "partial", "splitk"]
+    _fields_ = ([("prec", i32), ("training", i32), ("use_envelope", i32), ("D", i32), ("num_nodes", i32), ("_pad0", i32),
+                 ("num_edges", i64), ("radius", f32), ("eps", f32), ("momentum1", f32), ("momentum2", f32)]
+                + [(n, vp) for n in _PTRS1] + [("splitk_bytes", i64)])
+
+
 # name -> (restype, argtypes); every function listed here must be exported by the .so and
 # declared in include/cartnet_b200.h (tests/test_abi.py checks both directions).
 SIGNATURES = {
@@ -63,6 +78,10 @@ SIGNATURES = {
     "cartnet_segment_sum": (i32, [vp, i64, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "cartnet_dsilu_mul": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]),
     "cartnet_cast_rows": (i32, [vp, i64, vp, i64, i64, i32, i32, vp]),
+    "cartnet_layer_splitk_bytes": (i64, [i32, i32, i32, i64]),
+    "cartnet_layer_pack_weights": (i32, [C.POINTER(LayerDesc), vp]),
+    "cartnet_layer_fwd": (i32, [C.POINTER(LayerDesc), vp]),
+    "cartnet_layer_bwd": (i32, [C.POINTER(LayerDesc), vp]),
 }
 
 _lib = None

@@ -102,3 +102,52 @@ def collate(items) -> CrystalBatch:
     if ys:
         out.y = torch.cat(ys)
     return out
+
+
+class DevicePrefetcher:
+    """Iterates host batches (pinned memory) and hands out DEVICE batches one step ahead: the host->device copies
+    and the per-batch graph plan (int32 CSR views used by every layer) of batch i+1 are issued on a side stream while
+    batch i trains, so neither sits on the critical path of the step. This is the device-side counterpart of the
+    reference's DataLoader(pin_memory=True) + `batch.to("cuda:0")` (/root/reference/loader/loader.py:114-124,
+    train/train.py:169)."""
+
+    def __init__(self, batches, device, num_nodes_attr: str = "x"):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        from .cartnet import get_plan
+        try:
+            hb = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            b = CrystalBatch(**hb.__dict__).to(self.device, non_blocking=True)
+            if hasattr(b, "edge_index"):
+                get_plan(b)                     # cached by edge_index identity; the layers find it ready
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._next = (b, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        b, ev = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        tensors = list(b.__dict__.values())     # everything below was allocated on the side stream
+        if hasattr(b, "edge_index"):
+            from .cartnet import get_plan
+            tensors += list(get_plan(b).__dict__.values())
+        for v in tensors:
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(cur)
+        self._preload()
+        return b

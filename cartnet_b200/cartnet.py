@@ -250,7 +250,13 @@ class CartNet_layer(nn.Module, _PrecisionMixin):
                    radius=self.radius, use_envelope=self.use_envelope, holder=holder,
                    rm1=self.norm.running_mean, rv1=self.norm.running_var, momentum1=self._momentum(self.norm),
                    rm2=self.norm2.running_mean, rv2=self.norm2.running_var, momentum2=self._momentum(self.norm2))
-        x_out, e_out = CF.cartnet_layer(x, e, self._packed(), cfg)
+        if CF.USE_NATIVE_LAYER:      # one C-ABI call per direction (csrc/layer.cu)
+            params = (self.MLP_gate[0].weight, self.MLP_aggr[0].weight, self.MLP_gate[0].bias, self.MLP_aggr[0].bias,
+                      self.MLP_gate[2].weight, self.MLP_aggr[2].weight, self.MLP_gate[2].bias, self.MLP_aggr[2].bias,
+                      self.norm.weight, self.norm.bias, self.norm2.weight, self.norm2.bias)
+            x_out, e_out = CF.cartnet_layer_native(x, e, params, cfg)
+        else:                        # Python composition of the primitives (specification; CPU host-logic tests)
+            x_out, e_out = CF.cartnet_layer(x, e, self._packed(), cfg)
         if training:
             self.norm.num_batches_tracked += 1
             self.norm2.num_batches_tracked += 1

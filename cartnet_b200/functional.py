@@ -176,7 +176,8 @@ class _LayerFn(torch.autograd.Function):
         dP = torch.empty(N, 4 * D, dtype=T, device=dev)
         ops.segment_sum(dZ, plan.row_ptr, None, N, dP[:, :2 * D], prec)
         ops.segment_sum(dZ, plan.col_ptr, plan.perm_src, N, dP[:, 2 * D:], prec)
-        db1 = ops.colsum(dP[:, :2 * D], prec)        # sum_e dZ = sum_n (sum_{e -> n} dZ): N rows instead of E
+        # sum_e dZ = sum_n (sum_{e -> n} dZ): N rows instead of E (two D-wide reductions, as in csrc/layer.cu)
+        db1 = torch.cat([ops.colsum(dP[:, :D], prec), ops.colsum(dP[:, D:2 * D], prec)])
         dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
         ops.gemm(prec, dP, _to_t(W1n.t(), prec), resid=dx_out, out_f32=dx_in)
         dW1n = ops.gemm_tn(prec, dP, x_t)
@@ -186,6 +187,124 @@ class _LayerFn(torch.autograd.Function):
 
 
 def cartnet_layer(x, e, packed, cfg):
-    """packed = (W1n, W1e, b1, G2, A2, bg2, ba2, w1, b1n, w2, b2n). Returns x_out, e_out and fills
-    cfg['holder'] with the T-typed operand copies for the next layer."""
+    """Python composition of the primitive entry points (the executable specification of cartnet_layer_fwd/bwd;
+    used by the CPU host-logic tests with emulated primitives and by the GPU test that checks the native
+    orchestration is bit-identical to it). packed = (W1n, W1e, b1, G2, A2, bg2, ba2, w1, b1n, w2, b2n)."""
     return _LayerFn.apply(x, e, *packed, cfg)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# native orchestration: one C-ABI call per layer forward / backward (cartnet_b200/csrc/layer.cu)
+# ----------------------------------------------------------------------------------------------------------------
+USE_NATIVE_LAYER = True
+
+
+def _carve(buf, sizes_shapes):
+    out, off = [], 0
+    for shape in sizes_shapes:
+        n = 1
+        for d in shape:
+            n *= d
+        out.append(buf[off:off + n].view(*shape))
+        off += n
+    return out
+
+
+class _NativeLayerFn(torch.autograd.Function):
+    """inputs: x, e, then the module's own parameters in the reference layout
+       (G1, A1, bg1, ba1, G2, A2, bg2, ba2, bn1_w, bn1_b, bn2_w, bn2_b)."""
+
+    @staticmethod
+    def forward(ctx, x, e, G1, A1, bg1, ba1, G2, A2, bg2, ba2, w1, b1n, w2, b2n, cfg):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        prec, plan, dist, training = cfg["prec"], cfg["plan"], cfg["dist"], cfg["training"]
+        T = t_dtype(prec)
+        dev = x.device
+        if not x.is_cuda:
+            raise RuntimeError("cartnet_b200: CartNet_layer needs CUDA tensors (no CPU fallback exists)")
+        N, D = int(x.shape[0]), int(x.shape[1])
+        E = int(e.shape[0])
+        x = x.detach().contiguous()
+        e = e.detach().contiguous()
+        x_t, e_t = cfg.get("x_t"), cfg.get("e_t")
+        if x_t is None:
+            x_t = ops.cast(x, prec)
+        if e_t is None:
+            e_t = ops.cast(e, prec)
+        shadow = not f32_storage(prec)
+        DD = D * D
+        tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D, dtype=T, device=dev)
+        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H) = _carve(tbuf, [
+            (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D)])
+        fbuf = torch.empty(2 * E * D + N * D + 6 * D, dtype=torch.float32, device=dev)
+        g, s, m, mean1, var1, mean2, var2, b1 = _carve(fbuf, [(E, D), (E, D), (N, D), (D,), (D,), (D,), (D,), (2 * D,)])
+        x_out = torch.empty(N, D, dtype=torch.float32, device=dev)
+        e_out = torch.empty(E, D, dtype=torch.float32, device=dev)
+        x_out_t = torch.empty(N, D, dtype=T, device=dev) if shadow else None
+        e_out_t = torch.empty(E, D, dtype=T, device=dev) if shadow else None
+        part = ops._partial(dev, int(lib.cartnet_colstats_workspace(2 * D)))
+        L = _lib.LayerDesc()
+        L.prec, L.training, L.use_envelope, L.D = prec, int(training), int(bool(cfg["use_envelope"])), D
+        L.num_nodes, L.num_edges = N, E
+        L.radius, L.eps, L.momentum1, L.momentum2 = float(cfg["radius"]), ops.EPS_BN, float(cfg["momentum1"]), float(cfg["momentum2"])
+        p = ops._p
+        L.src32, L.dst32, L.row_ptr, L.col_ptr, L.perm_src = p(plan.src32), p(plan.dst32), p(plan.row_ptr), p(plan.col_ptr), p(plan.perm_src)
+        L.dist, L.x, L.e, L.x_t, L.e_t = p(dist), p(x), p(e), p(x_t), p(e_t)
+        params = dict(G1=G1, A1=A1, bg1=bg1, ba1=ba1, G2=G2, A2=A2, bg2=bg2, ba2=ba2, bn1_w=w1, bn1_b=b1n, bn2_w=w2, bn2_b=b2n)
+        for k, v in params.items():
+            setattr(L, k, p(v.detach()))
+        L.bn1_rm, L.bn1_rv, L.bn2_rm, L.bn2_rv = p(cfg["rm1"]), p(cfg["rv1"]), p(cfg["rm2"]), p(cfg["rv2"])
+        for k, v in dict(W1n_t=W1n_t, W1e_t=W1e_t, G2_t=G2_t, A2_t=A2_t, W1nT_t=W1nT_t, W1eT_t=W1eT_t, G2T_t=G2T_t, A2T_t=A2T_t,
+                         b1=b1, P=P, Z=Z, H=H, g=g, s=s, m=m, mean1=mean1, var1=var1, mean2=mean2, var2=var2, x_out=x_out,
+                         e_out=e_out, x_out_t=x_out_t, e_out_t=e_out_t, partial=part).items():
+            setattr(L, k, p(v))
+        st = ops._stream()
+        _lib.check(lib.cartnet_layer_pack_weights(C.byref(L), st), "layer_pack_weights")
+        _lib.check(lib.cartnet_layer_fwd(C.byref(L), st), "layer_fwd")
+        cfg["holder"]["x_t"] = x_out_t if shadow else x_out
+        cfg["holder"]["e_t"] = e_out_t if shadow else e_out
+        ctx.L = L
+        ctx.keep = (x, e, x_t, e_t, tbuf, fbuf, dist, plan, cfg["rm1"], cfg["rv1"], cfg["rm2"], cfg["rv2"]) + tuple(
+            v.detach() for v in params.values())
+        ctx.dims = (N, E, D, prec)
+        return x_out, e_out
+
+    @staticmethod
+    def backward(ctx, dx_out, de_out):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        L = ctx.L
+        N, E, D, prec = ctx.dims
+        T = t_dtype(prec)
+        dev = ctx.keep[0].device
+        dx_out = torch.zeros(N, D, dtype=torch.float32, device=dev) if dx_out is None else dx_out.contiguous()
+        de_out = torch.zeros(E, D, dtype=torch.float32, device=dev) if de_out is None else de_out.contiguous()
+        tbuf = torch.empty(2 * E * D + E * 2 * D + N * 4 * D, dtype=T, device=dev)
+        ds_t, dg_t, dZ, dP = _carve(tbuf, [(E, D), (E, D), (E, 2 * D), (N, 4 * D)])
+        fbuf = torch.empty(N * D + E * D + 5 * D, dtype=torch.float32, device=dev)
+        dm, dghat, sums1, sums2 = _carve(fbuf, [(N, D), (E, D), (3 * D,), (2 * D,)])
+        dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
+        de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
+        gbuf = torch.empty(8 * D * D + 8 * D, dtype=torch.float32, device=dev)
+        (dG1, dA1, dG2, dA2, dbg1, dba1, dbg2, dba2, dw1, db1n, dw2, db2n) = _carve(gbuf, [
+            (D, 3 * D), (D, 3 * D), (D, D), (D, D), (D,), (D,), (D,), (D,), (D,), (D,), (D,), (D,)])
+        nbytes = int(lib.cartnet_layer_splitk_bytes(prec, D, N, E))
+        ws = ops._workspace(dev, nbytes)
+        part = ops._partial(dev, int(lib.cartnet_colstats_workspace(2 * D)))
+        p = ops._p
+        for k, v in dict(dx_out=dx_out, de_out=de_out, dm=dm, ds_t=ds_t, dg_t=dg_t, dghat=dghat, dZ=dZ, dP=dP, sums1=sums1,
+                         sums2=sums2, dx_in=dx_in, de_in=de_in, dG1=dG1, dA1=dA1, dbg1=dbg1, dba1=dba1, dG2=dG2, dA2=dA2,
+                         dbg2=dbg2, dba2=dba2, dbn1_w=dw1, dbn1_b=db1n, dbn2_w=dw2, dbn2_b=db2n, partial=part, splitk=ws).items():
+            setattr(L, k, p(v))
+        L.splitk_bytes = ws.numel() * 4
+        _lib.check(lib.cartnet_layer_bwd(C.byref(L), ops._stream()), "layer_bwd")
+        ctx.keep = None
+        return dx_in, de_in, dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n, None
+
+
+def cartnet_layer_native(x, e, params, cfg):
+    """params = (G1, A1, bg1, ba1, G2, A2, bg2, ba2, bn1_w, bn1_b, bn2_w, bn2_b) in the reference's own layout."""
+    return _NativeLayerFn.apply(x, e, *params, cfg)

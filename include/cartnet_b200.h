@@ -226,6 +226,58 @@ int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz
 int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C,
                       int32_t prec, cartnet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Whole-layer entry points -- CartNet_layer.forward (models/cartnet.py:204-274) and its backward as ONE call
+ * each: the host issues the same kernels as the primitives above in a fixed order, without returning to the
+ * caller's language in between. All buffers (saved activations, scratch, outputs) are caller-allocated.
+ * D = dim_in; T as above. Weight layout of the reference is kept: G1/A1 = MLP_gate[0]/MLP_aggr[0].weight [D,3D]
+ * with columns [x_i | x_j | e] (cartnet.py:237), G2/A2 = MLP_*[2].weight [D,D].
+ * ------------------------------------------------------------------------------------- */
+typedef struct cartnet_layer {
+    int32_t prec, training, use_envelope, D;
+    int32_t num_nodes, _pad0;
+    int64_t num_edges;
+    float radius, eps, momentum1, momentum2;
+    /* graph (dst-sorted edges) */
+    const int32_t *src32, *dst32, *row_ptr, *col_ptr, *perm_src;
+    const float* dist;                               /* [E] */
+    /* layer inputs: fp32 residual streams and their T-typed operand copies (may alias when T = float) */
+    const float *x, *e;
+    const void *x_t, *e_t;
+    /* parameters (fp32, reference layout) */
+    const float *G1, *A1, *bg1, *ba1, *G2, *A2, *bg2, *ba2, *bn1_w, *bn1_b, *bn2_w, *bn2_b;
+    float *bn1_rm, *bn1_rv, *bn2_rm, *bn2_rv;        /* running statistics, updated in place when training */
+    /* T-typed packed weights, filled by cartnet_layer_pack_weights:
+     * W1n [4D,D] = [G1_i;A1_i;G1_j;A1_j], W1e [2D,D] = [G1_e;A1_e], G2t/A2t [D,D] copies, and the transposes
+     * W1nT [D,4D], W1eT [D,2D], G2T, A2T [D,D] used by the dgrad GEMMs; b1 [2D] = [bg1;ba1] fp32 */
+    void *W1n_t, *W1e_t, *G2_t, *A2_t, *W1nT_t, *W1eT_t, *G2T_t, *A2T_t;
+    float* b1;
+    /* forward: saved activations and outputs */
+    void *P, *Z, *H;                                 /* T: [N,4D], [E,2D], [E,2D] */
+    float *g, *s, *m;                                /* [E,D], [E,D], [N,D] */
+    float *mean1, *var1, *mean2, *var2;              /* [D] statistics used (batch or running) */
+    float *x_out, *e_out;                            /* [N,D], [E,D] */
+    void *x_out_t, *e_out_t;                         /* T copies for the next layer (null when T = float) */
+    /* backward: inputs, scratch, outputs */
+    const float *dx_out, *de_out;
+    float* dm;                                       /* [N,D] */
+    void *ds_t, *dg_t;                               /* T [E,D] */
+    float* dghat;                                    /* [E,D] */
+    void *dZ, *dP;                                   /* T [E,2D], [N,4D] */
+    float *sums1, *sums2;                            /* [3D], [2D] */
+    float *dx_in, *de_in;                            /* [N,D], [E,D] */
+    float *dG1, *dA1, *dbg1, *dba1, *dG2, *dA2, *dbg2, *dba2, *dbn1_w, *dbn1_b, *dbn2_w, *dbn2_b;
+    /* workspaces */
+    double* partial;                                 /* >= cartnet_colstats_workspace(2D) */
+    float* splitk;                                   /* >= cartnet_layer_splitk_bytes(...) */
+    int64_t splitk_bytes;
+} cartnet_layer_t;
+
+int64_t cartnet_layer_splitk_bytes(int32_t prec, int32_t D, int32_t num_nodes, int64_t num_edges);
+int cartnet_layer_pack_weights(const cartnet_layer_t* L /* host */, cartnet_stream_t stream);
+int cartnet_layer_fwd(const cartnet_layer_t* L /* host */, cartnet_stream_t stream);
+int cartnet_layer_bwd(const cartnet_layer_t* L /* host */, cartnet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -186,7 +186,8 @@ ALL = ["graph_plan", "edge_features", "gemm", "gemm_tn", "colstats", "colsum", "
 def install(monkeypatch):
     """Route cartnet_b200.ops through this module (CPU host-logic tests only)."""
     import sys
-    from cartnet_b200 import ops
+    from cartnet_b200 import functional, ops
     me = sys.modules[__name__]
+    monkeypatch.setattr(functional, "USE_NATIVE_LAYER", False)   # Python composition = spec of cartnet_layer_fwd/bwd
     for name in ALL:
         monkeypatch.setattr(ops, name, getattr(me, name))

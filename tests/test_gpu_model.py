@@ -123,6 +123,26 @@ def test_larger_batch_against_oracle_and_determinism(precision):
         assert torch.equal(got["grads"][k], got2["grads"][k]), k
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_native_layer_orchestration_is_bit_identical_to_python_composition(monkeypatch, precision):
+    """cartnet_layer_fwd / cartnet_layer_bwd (csrc/layer.cu) issue the same kernels in the same order as the Python
+    composition of the primitives (cartnet_b200/functional.py::_LayerFn, the version the CPU host-logic tests check
+    against the reference goldens): outputs, gradients and BatchNorm buffers must agree bit for bit."""
+    from cartnet_b200 import functional as CF
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
+    batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
+    res = {}
+    for native in (True, False):
+        monkeypatch.setattr(CF, "USE_NATIVE_LAYER", native)
+        res[native] = common.run_train_step(_model(kw, seed, lrad, precision), batch0)
+    a, b = res[True], res[False]
+    assert torch.equal(a["pred"], b["pred"]) and torch.equal(a["pred_eval"], b["pred_eval"]) and torch.equal(a["e"], b["e"])
+    for k in b["grads"]:
+        assert torch.equal(a["grads"][k], b["grads"][k]), k
+    for k in b["bufs"]:
+        assert torch.equal(a["bufs"][k], b["bufs"][k]), k
+
+
 def test_unsorted_edges_and_layer_standalone():
     name = "adp"
     shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
