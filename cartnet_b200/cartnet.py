@@ -120,6 +120,39 @@ class _PackW1(torch.autograd.Function):
         return dG1, dA1
 
 
+class _BroadcastRows(torch.autograd.Function):
+    """rows[B, C] -> rows[batch] ([N, C]) for a SORTED batch vector (nodes are grouped by crystal). Forward is the
+    same gather as `t[batch.batch]` (cartnet.py:145); backward is a deterministic segmented sum over each crystal's
+    contiguous node range (C-ABI cartnet_segment_sum) instead of torch's sort-based index_put accumulation."""
+
+    @staticmethod
+    def forward(ctx, rows, batch_vec, natoms):
+        num_graphs = int(natoms.numel())
+        ptr = torch.zeros(num_graphs + 1, dtype=torch.int32, device=rows.device)
+        ptr[1:] = torch.cumsum(natoms.to(rows.device), 0).to(torch.int32)      # no host sync (bincount would need one)
+        ctx.save_for_backward(ptr)
+        ctx.num_graphs = num_graphs
+        return rows.index_select(0, batch_vec)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ptr,) = ctx.saved_tensors
+        grad = grad.contiguous()
+        out = torch.empty(ctx.num_graphs, grad.shape[1], dtype=torch.float32, device=grad.device)
+        ops.segment_sum(grad, ptr, None, ctx.num_graphs, out, PREC_FP32)
+        return out, None, None
+
+
+def _per_graph_rows(rows, batch):
+    """rows[batch.batch]; uses the deterministic segmented backward when the number of graphs is known without a
+    device->host read (PyG batches carry num_graphs / natoms) and the channel count fits the kernel."""
+    nat = getattr(batch, "natoms", None)
+    c = int(rows.shape[1])
+    if rows.is_cuda and nat is not None and int(nat.numel()) == int(rows.shape[0]) and c % 4 == 0 and c // 4 <= 256 and 256 % (c // 4) == 0:
+        return _BroadcastRows.apply(rows, batch.batch, nat)
+    return rows[batch.batch]
+
+
 class _PrecisionMixin:
     def set_precision(self, precision: str):
         if precision not in _PRECISIONS:
@@ -174,11 +207,11 @@ class Encoder(nn.Module, _PrecisionMixin):
 
     def forward(self, batch):
         if self.temperature and self.atom_types:                                   # cartnet.py:144-151
-            x = self.embedding(batch.x) + self.temperature_proj_atom(batch.temperature.unsqueeze(-1))[batch.batch]
+            x = self.embedding(batch.x) + _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
         elif not self.temperature and self.atom_types:
             x = self.embedding(batch.x) + self.bias
         elif self.temperature and not self.atom_types:
-            x = self.temperature_proj_atom(batch.temperature.unsqueeze(-1))[batch.batch]
+            x = _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
         else:
             batch.x = self.embedding.weight.repeat(batch.x.shape[0], 1)
         if self.temperature or self.atom_types:
@@ -282,10 +315,13 @@ class Cholesky_head(nn.Module):
         if idx is None:
             idx = _mask_index(batch.non_H_mask)
         pred = self.MLP(batch.x.index_select(0, idx))                                # == batch.x[batch.non_H_mask]
-        diag = F.softplus(pred[:, :3])
-        L = torch.zeros(pred.size(0), 3, 3, device=pred.device, dtype=pred.dtype)
-        L[:, [0, 1, 2], [0, 1, 2]] = diag
-        L[:, [0, 0, 1], [1, 2, 2]] = pred[:, 3:]
+        d = F.softplus(pred[:, :3])
+        z = torch.zeros_like(d[:, 0])
+        # upper-triangular L with softplus diagonal (cartnet.py:296-301), assembled with stack instead of advanced
+        # indexing: index tensors built from Python lists would be copied host->device (a sync) on every call
+        L = torch.stack([torch.stack([d[:, 0], pred[:, 3], pred[:, 4]], dim=-1),
+                         torch.stack([z, d[:, 1], pred[:, 5]], dim=-1),
+                         torch.stack([z, z, d[:, 2]], dim=-1)], dim=1)
         return torch.bmm(L.transpose(1, 2), L), batch.y
 
 

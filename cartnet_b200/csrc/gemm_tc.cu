@@ -630,8 +630,9 @@ static bool tn_plan(int prec, int M, int N, int64_t K, TnPlan* p) {
     p->kblks_total = (int)ceil_div64(K > 0 ? K : 1, boxw);      // KROWS == boxw for both types
     const int problems = p->n_blocks * p->m_blocks;
     int s = kNumSMs / problems;
+    const int by_k = p->kblks_total / 16;          // at least 16 k-blocks per split: partials must not outweigh the operands
+    if (s > by_k) s = by_k;
     if (s < 1) s = 1;
-    if (s > p->kblks_total) s = p->kblks_total;
     p->kblks_per_split = ceil_div(p->kblks_total, s);
     p->splits = ceil_div(p->kblks_total, p->kblks_per_split);
     return true;
