@@ -356,7 +356,11 @@ def run_ours(args):
     else:
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    roof.update({"traffic": None, "kernel": top_key, "launches_per_step": top["n"] / 2, "avg_launch_ms": top["ms"] / top["n"],
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(tp) and args.precision == "bf16" and args.batch == 64:
+        traffic = json.load(open(tp)).get(top_key)      # DRAM bytes per launch of this op from the committed ncu capture
+    roof.update({"traffic": traffic, "kernel": top_key, "launches_per_step": top["n"] / 2, "avg_launch_ms": top["ms"] / top["n"],
                  "share_of_step": top["ms"] / tot_ms, "peak_source": pk["src"] + (" (sustained bf16)" if top["flops"] > 0 else "")})
     breakdown = {k: round(v["ms"] / 2, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
     step_s = ms_step * 1e-3
