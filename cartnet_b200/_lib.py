@@ -60,6 +60,7 @@ SIGNATURES = {
     "cartnet_nlist_count": (i32, [vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, vp]),
     "cartnet_exclusive_scan_i32": (i32, [vp, i32, vp, vp]),
     "cartnet_nlist_fill": (i32, [vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cartnet_nlist_knn_mask": (i32, [vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]),
     "cartnet_graph_split": (i32, [vp, i64, i32, vp, vp, vp, vp]),
     "cartnet_graph_csr": (i32, [vp, i64, i32, vp, vp, vp, vp]),
     "cartnet_edge_features": (i32, [vp, vp, vp, vp, i32, f32, i32, i64, vp, i32, i32, vp]),

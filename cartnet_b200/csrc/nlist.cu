@@ -292,6 +292,61 @@ __global__ void __launch_bounds__(128) group_sort_kernel(const int32_t* __restri
     }
 }
 
+// kNN cap: one warp per destination row (see cartnet_nlist_knn_mask in the header)
+__global__ void __launch_bounds__(128)
+knn_mask_kernel(const float* __restrict__ direction, const int32_t* __restrict__ row_ptr, int num_nodes, int threshold,
+                float tolerance, int strict, float* __restrict__ d2s, uint8_t* __restrict__ keep, int32_t* __restrict__ new_count) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= num_nodes) return;
+    const int b0 = row_ptr[n], cnt = row_ptr[n + 1] - b0;
+    if (cnt <= threshold) {          // cutoff would be inf (utils.py:294,322): everything stays
+        for (int i = lane; i < cnt; i += 32) keep[b0 + i] = 1;
+        if (lane == 0) new_count[n] = cnt;
+        return;
+    }
+    for (int i = lane; i < cnt; i += 32) {
+        const float* v = direction + 3 * (int64_t)(b0 + i);
+        d2s[b0 + i] = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));   // utils.py:197
+    }
+    __syncwarp();
+    const float* d2 = d2s + b0;
+    // stable rank of every entry; the entry with rank == threshold carries the (threshold+1)-th smallest value
+    float vk = 0.f;
+    int kept = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        int rank = 0x7fffffff;
+        float mine = 0.f;
+        if (i < cnt) {
+            mine = d2[i];
+            rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float o = d2[j];
+                rank += (o < mine || (o == mine && j < i)) ? 1 : 0;
+            }
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, rank == threshold);
+        if (hit) vk = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+        if (strict && i < cnt) {
+            const int k = rank < threshold ? 1 : 0;
+            keep[b0 + i] = (uint8_t)k;
+            kept += k;
+        }
+    }
+    if (!strict) {
+        const float cutoff = __fadd_rn(vk, tolerance);            // utils.py:322-326
+        for (int i = lane; i < cnt; i += 32) {
+            const int k = d2[i] <= cutoff ? 1 : 0;
+            keep[b0 + i] = (uint8_t)k;
+            kept += k;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    if (lane == 0) new_count[n] = kept;
+}
+
 }  // namespace cartnet
 
 using namespace cartnet;
@@ -340,6 +395,17 @@ int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* cryst
     nlist_kernel<true><<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(
         pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, nullptr, row_ptr,
         edge_index, num_edges, unit_cell, dist, direction, cart_dist, cart_dir, src32, dst32);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_nlist_knn_mask(const float* direction, const int32_t* row_ptr, int32_t num_nodes, int32_t threshold, float tolerance,
+                           int32_t strict, float* d2_scratch, uint8_t* keep, int32_t* new_row_count, cartnet_stream_t stream) {
+    CN_CHECK_ARG(row_ptr && keep && new_row_count && d2_scratch && threshold > 0, "nlist_knn_mask: bad arguments");
+    if (num_nodes <= 0) return 0;
+    CN_CHECK_ARG(direction, "nlist_knn_mask: null direction");
+    knn_mask_kernel<<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(direction, row_ptr, num_nodes, threshold, tolerance,
+                                                                             strict, d2_scratch, keep, new_row_count);
     CN_LAUNCH_CHECK();
     return 0;
 }

@@ -130,6 +130,19 @@ def nlist_build(pos, cell, natoms, radius: float, pbc_mask: int = 7, batch_max_r
     return out
 
 
+def nlist_knn_mask(direction, row_ptr, num_nodes: int, threshold: int, tolerance: float = 0.01, strict: bool = False):
+    """Boolean keep-mask [E] of the kNN neighbour cap (dataset/utils.py:240-360) for a dst-sorted graph."""
+    lib = _lib.load()
+    direction = _req(direction.contiguous(), torch.float32, "direction")
+    E = int(direction.shape[0])
+    keep = torch.empty(E, dtype=torch.uint8, device=direction.device)
+    scratch = torch.empty(max(E, 1), dtype=torch.float32, device=direction.device)
+    counts = torch.empty(num_nodes, dtype=torch.int32, device=direction.device)
+    _lib.check(lib.cartnet_nlist_knn_mask(_p(direction), _p(row_ptr), num_nodes, int(threshold), float(tolerance), int(bool(strict)),
+                                          _p(scratch), _p(keep), _p(counts), _stream()), "nlist_knn_mask")
+    return keep.bool(), counts
+
+
 @dataclass
 class GraphPlan:
     """int32 indexing for the layer kernels; built once per batch and reused by all layers."""

@@ -29,14 +29,17 @@ def radius_graph_pbc(data, radius, max_num_neighbors_threshold=None, enforce_max
                      pbc=[True, True, True]):
     """Returns (edge_index [2,E] i64, unit_cell [E,3] f32, dist [E] f32, direction [E,3] f32).
     `data` needs .pos [N,3], .cell [B,3,3], .natoms [B] (and optionally .pbc); tensors must be on a
-    CUDA device. Like the reference, a multi-crystal call searches max(rep) cells for every crystal."""
-    if max_num_neighbors_threshold is not None and max_num_neighbors_threshold > 0:
-        raise NotImplementedError(
-            "the kNN neighbour cap (dataset/utils.py:240-360) is not on the CartNet path "
-            "(main.py:176 sets max_neighbours=-1); see DESIGN.md, scope row (f)2")
+    CUDA device. Like the reference, a multi-crystal call searches max(rep) cells for every crystal.
+    `max_num_neighbors_threshold` applies the reference's kNN cap (degenerate neighbours within 0.01 A^2 of the cut are
+    kept together unless `enforce_max_neighbors_strictly`)."""
     out = ops.nlist_build(data.pos, data.cell, data.natoms, float(radius), pbc_mask=_pbc_mask(data, pbc),
                           batch_max_reps=True, want_cart=False)
-    return out["edge_index"], out["unit_cell"], out["dist"], out["direction"]
+    ei, uc, dist, direction = out["edge_index"], out["unit_cell"], out["dist"], out["direction"]
+    if max_num_neighbors_threshold is not None and max_num_neighbors_threshold > 0:     # utils.py:215-233
+        keep, _ = ops.nlist_knn_mask(direction, out["row_ptr"], int(data.pos.shape[0]), int(max_num_neighbors_threshold),
+                                     strict=enforce_max_neighbors_strictly)
+        ei, uc, dist, direction = ei[:, keep], uc[keep], dist[keep], direction[keep]    # masked_select, like the reference
+    return ei, uc, dist, direction
 
 
 def build_graph(pos, cell, natoms, radius: float = 5.0, pbc=(True, True, True)):

@@ -74,6 +74,15 @@ int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* cryst
                        float* direction, float* cart_dist, float* cart_dir, int32_t* src32,
                        int32_t* dst32, cartnet_stream_t stream);
 
+/* kNN neighbour cap -- replaces get_max_neighbors_mask (dataset/utils.py:240-360, call at :215-233).
+ * For every destination row of a dst-sorted graph: keep[e] = 1 iff the row has <= threshold edges, or (non-strict)
+ * d2[e] <= (threshold+1)-th smallest d2 of the row + tolerance (degenerate neighbours stay together), or (strict)
+ * e is among the `threshold` smallest (ties by edge order). d2 is recomputed from `direction` with the reference's
+ * rounding ((dx*dx+dy*dy)+dz*dz, no FMA). d2_scratch: float[E]; new_row_count[n] = kept edges of row n. */
+int cartnet_nlist_knn_mask(const float* direction, const int32_t* row_ptr, int32_t num_nodes, int32_t threshold,
+                           float tolerance, int32_t strict, float* d2_scratch, uint8_t* keep,
+                           int32_t* new_row_count, cartnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Graph plan for the layer kernels -- replaces PyG MessagePassing's lift/scatter indexing
  * (call at models/cartnet.py:218-221) and torch_scatter.scatter (cartnet.py:259).

@@ -19,9 +19,16 @@ def scatter(src, index, dim=0, out=None, dim_size=None, reduce="sum"):
     raise NotImplementedError(reduce)
 
 
-def segment_coo(*a, **k):  # import-only placeholder (kNN cap, not on the CartNet path)
-    raise NotImplementedError
+def segment_coo(src, index, out=None, dim_size=None, reduce="sum"):
+    """sum of src over sorted `index` (torch_scatter.segment_coo, used at dataset/utils.py:269)."""
+    assert reduce == "sum" and src.dim() == 1
+    if dim_size is None:
+        dim_size = int(index.max()) + 1
+    return torch.zeros(int(dim_size), dtype=src.dtype, device=src.device).scatter_add_(0, index, src)
 
 
-def segment_csr(*a, **k):
-    raise NotImplementedError
+def segment_csr(src, indptr, out=None, reduce="sum"):
+    """sum of src over [indptr[i], indptr[i+1]) (torch_scatter.segment_csr, used at dataset/utils.py:280,342)."""
+    assert reduce == "sum" and src.dim() == 1
+    c = torch.cat([src.new_zeros(1), torch.cumsum(src, 0)])
+    return c[indptr[1:]] - c[indptr[:-1]]

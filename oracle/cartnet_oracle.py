@@ -88,7 +88,7 @@ def cell_offsets(cell, reps, mode=None):
 
 
 def radius_graph_pbc_oracle(pos, cell, natoms, radius, pbc=(True, True, True), chunk_rows=64,
-                            reps=None):
+                            reps=None, max_num_neighbors_threshold=None, enforce_max_neighbors_strictly=False):
     """Restates radius_graph_pbc (dataset/utils.py:57-237) with max_num_neighbors_threshold=None.
 
     pos [N,3] f32, cell [B,3,3] f32 (rows = lattice vectors), natoms [B] int.
@@ -131,8 +131,41 @@ def radius_graph_pbc_oracle(pos, cell, natoms, radius, pbc=(True, True, True), c
         return np.stack([z, z]), np.zeros((0, 3), f32), np.zeros((0,), f32), np.zeros((0, 3), f32)
     src = np.concatenate(src_l)
     dst = np.concatenate(dst_l)
-    return (np.stack([src, dst]), np.concatenate(uc_l).astype(f32),
-            np.sqrt(np.concatenate(d2_l)).astype(f32), np.concatenate(dir_l).astype(f32))
+    uc, d2, direc = np.concatenate(uc_l).astype(f32), np.concatenate(d2_l).astype(f32), np.concatenate(dir_l).astype(f32)
+    if max_num_neighbors_threshold is not None:                                    # :215-233
+        keep = max_neighbors_mask_oracle(dst, d2, int(natoms.sum()), max_num_neighbors_threshold,
+                                         enforce_max_strictly=enforce_max_neighbors_strictly)
+        src, dst, uc, d2, direc = src[keep], dst[keep], uc[keep], d2[keep], direc[keep]
+    return np.stack([src, dst]), uc, np.sqrt(d2).astype(f32), direc
+
+
+def max_neighbors_mask_oracle(dst, d2, num_nodes, threshold, degeneracy_tolerance=0.01, enforce_max_strictly=False):
+    """Restates get_max_neighbors_mask (dataset/utils.py:240-360) for dst-sorted edges: per atom keep the edges whose
+    SQUARED distance is <= (the (threshold+1)-th smallest squared distance of that atom) + tolerance, i.e. degenerate
+    neighbours are kept together (:322-329); atoms with <= threshold edges keep everything (their cutoff is inf).
+    Strict mode keeps the `threshold` smallest (:316-319; ties broken by edge order here -- torch.sort leaves them
+    unspecified). If no atom exceeds the threshold, or threshold <= 0, everything is kept (:283-290)."""
+    dst = np.asarray(dst)
+    d2 = np.asarray(d2, dtype=f32)
+    counts = np.bincount(dst, minlength=num_nodes)
+    keep = np.ones(len(dst), dtype=bool)
+    if threshold is None or threshold <= 0 or counts.max(initial=0) <= threshold:
+        return keep
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    for n in range(num_nodes):
+        lo, hi = starts[n], starts[n + 1]
+        if hi - lo <= threshold:
+            continue
+        row = d2[lo:hi]
+        order = np.argsort(row, kind="stable")
+        if enforce_max_strictly:
+            k = np.zeros(hi - lo, dtype=bool)
+            k[order[:threshold]] = True
+        else:
+            cutoff = f32(row[order[threshold]] + f32(degeneracy_tolerance))
+            k = row <= cutoff
+        keep[lo:hi] = k
+    return keep
 
 
 def edge_vectors(direction: torch.Tensor):

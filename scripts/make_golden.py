@@ -65,6 +65,16 @@ def graph_cases():
     cases["adp700"] = dict(pos=p, cell=c[None], natoms=[700], radius=5.0, hash_only=True)
     p, c = synth(8, 40.0, 12)   # sparse: some atoms may have few neighbours
     cases["sparse8"] = dict(pos=p, cell=c[None], natoms=[8], radius=2.5)
+    # kNN neighbour cap (dataset/utils.py:215-233,240-360) -- the path compute_knn / the Comformer baselines use
+    p, c = synth(60, 9.5, 1)
+    cases["knn12_adp60"] = dict(pos=p, cell=c[None], natoms=[60], radius=5.0, knn=12)
+    cases["knn25_adp60"] = dict(pos=p, cell=c[None], natoms=[60], radius=5.0, knn=25)
+    cases["knn200_adp60"] = dict(pos=p, cell=c[None], natoms=[60], radius=5.0, knn=200)          # nothing exceeds -> all kept
+    cases["knn6_cubic2"] = dict(pos=np.array([[0, 0, 0], [1.5, 1.5, 1.5]], np.float32),          # highly degenerate shells
+                                cell=(np.eye(3, dtype=np.float32) * 3.0)[None], natoms=[2], radius=5.0, knn=6)
+    p1, c1 = synth(12, 15.0, 5)
+    p2, c2 = synth(33, 9.5, 6)
+    cases["knn16_batch2"] = dict(pos=np.concatenate([p1, p2]), cell=np.stack([c1, c2]), natoms=[12, 33], radius=5.0, knn=16)
     return cases
 
 
@@ -74,9 +84,10 @@ def run_graph(dutils):
         data = SimpleNamespace(pos=torch.from_numpy(cs["pos"]), cell=torch.from_numpy(cs["cell"]),
                                natoms=torch.tensor(cs["natoms"], dtype=torch.int64),
                                pbc=torch.tensor([[True, True, True]]))
-        ei, uc, dist, direc = dutils.radius_graph_pbc(data, cs["radius"], None, pbc=[True, True, True])
+        ei, uc, dist, direc = dutils.radius_graph_pbc(data, cs["radius"], cs.get("knn"), pbc=[True, True, True])
         ei, uc, dist, direc = ei.numpy(), uc.numpy(), dist.numpy(), direc.numpy()
-        oei, ouc, odist, odir = O.radius_graph_pbc_oracle(cs["pos"], cs["cell"], cs["natoms"], cs["radius"])
+        oei, ouc, odist, odir = O.radius_graph_pbc_oracle(cs["pos"], cs["cell"], cs["natoms"], cs["radius"],
+                                                          max_num_neighbors_threshold=cs.get("knn"))
         assert np.array_equal(ei, oei), name
         assert np.array_equal(uc, ouc), name
         # torch.sqrt on this host is MKL VML (<=0.54 ulp, not correctly rounded): the oracle / CUDA
@@ -93,6 +104,7 @@ def run_graph(dutils):
         out[pre + "pos"], out[pre + "cell"] = cs["pos"], cs["cell"]
         out[pre + "natoms"] = np.asarray(cs["natoms"], np.int64)
         out[pre + "radius"] = np.float64(cs["radius"])
+        out[pre + "knn"] = np.int64(cs.get("knn") or 0)
         out[pre + "num_edges"] = np.int64(ei.shape[1])
         out[pre + "sha_edge_index"] = sha(ei)
         out[pre + "sha_unit_cell"] = sha(uc)

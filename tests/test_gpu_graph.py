@@ -23,7 +23,7 @@ def test_golden_graphs_bit_exact(golden_graph):
     for name in common.graph_case_names(g):
         pre = name + "/"
         ei, uc, dist, direc = radius_graph_pbc(_data(g[pre + "pos"], g[pre + "cell"], g[pre + "natoms"]),
-                                               float(g[pre + "radius"]), None)
+                                               float(g[pre + "radius"]), int(g[pre + "knn"]) or None)
         ei, uc, dist, direc = ei.cpu().numpy(), uc.cpu().numpy(), dist.cpu().numpy(), direc.cpu().numpy()
         assert ei.shape[1] == int(g[pre + "num_edges"]), name
         assert common.sha(ei) == str(g[pre + "sha_edge_index"]), name
@@ -58,6 +58,38 @@ def test_batched_build_equals_per_crystal_oracle(shape, count, seed):
     assert np.array_equal(out["dst32"].cpu().numpy(), ei[1].astype(np.int32))
     rp = out["row_ptr"].cpu().numpy()
     assert np.array_equal(np.diff(rp), np.bincount(ei[1], minlength=off))
+
+
+def test_random_cells_sweep_bit_exact():
+    """120 random crystals in one batched launch: skewed triclinic cells, tiny cells that need up to 6 repeats per axis
+    (both bmm summation orders, C from 27 to > 1000 cells), atoms outside the cell, radii 2.5..7 -- against the oracle run
+    per crystal (what the reference's data sets do)."""
+    rng = np.random.default_rng(1234)
+    cs = set()
+    for radius in (2.5, 5.0, 7.0):
+        pos_l, cell_l, nat = [], [], []
+        for i in range(40):
+            n = int(rng.integers(1, 24))
+            a = rng.uniform(1.6, 9.0)
+            cell = (np.diag(rng.uniform(0.7, 1.4, 3)) * a + rng.uniform(-0.35, 0.35, (3, 3)) * a * np.tri(3, k=-1)).astype(np.float32)
+            if i % 5 == 0:
+                cell = cell[[1, 2, 0]] * np.float32(-1 if i % 10 == 0 else 1)          # permuted / left-handed lattices
+            frac = rng.uniform(-0.4, 1.4, (n, 3))
+            pos_l.append((frac @ cell.astype(np.float64)).astype(np.float32)); cell_l.append(cell); nat.append(n)
+        out = build_graph(torch.from_numpy(np.concatenate(pos_l)).cuda(), torch.from_numpy(np.stack(cell_l)).cuda(),
+                          torch.tensor(nat).cuda(), radius)
+        eis, ucs, dirs = [], [], []
+        off = 0
+        for p, c, n in zip(pos_l, cell_l, nat):
+            ei, uc, d, v = O.radius_graph_pbc_oracle(p, c[None], [n], radius)
+            r = O.cell_repeats(c, radius)
+            cs.add((2 * r[0] + 1) * (2 * r[1] + 1) * (2 * r[2] + 1))
+            eis.append(ei + off); ucs.append(uc); dirs.append(v)
+            off += n
+        assert np.array_equal(out["edge_index"].cpu().numpy(), np.concatenate(eis, 1))
+        assert np.array_equal(out["unit_cell"].cpu().numpy(), np.concatenate(ucs))
+        assert np.array_equal(out["direction"].cpu().numpy().view(np.uint32), np.concatenate(dirs).view(np.uint32))
+    assert min(cs) == 27 and max(cs) > 400      # both bmm summation orders and large repeat counts were exercised
 
 
 def test_multi_crystal_call_uses_batch_max_reps():
@@ -116,3 +148,20 @@ def test_scan_and_csr_primitives():
             assert torch.equal(getattr(plan, f).cpu(), getattr(ref, f)), (n, E, f)
     with pytest.raises(IndexError):
         ops.graph_plan(torch.tensor([[0, 5], [1, 0]]).cuda(), 3)
+
+
+def test_knn_cap_against_oracle_random():
+    """kNN cap (dataset/utils.py:240-360) on larger random crystals: non-strict (the reference default, bit-exact by
+    construction: a value threshold) and strict (ties by edge order) against the oracle."""
+    rng = np.random.default_rng(77)
+    for n, k in ((150, 12), (90, 25), (40, 3)):
+        pos, cell = synthetic.make_crystal(n, 9.5, rng)
+        for strict in (False, True):
+            ei, uc, dist, direc = radius_graph_pbc(_data(pos, cell[None], [n]), 5.0, k, enforce_max_neighbors_strictly=strict)
+            oei, ouc, odist, odir = O.radius_graph_pbc_oracle(pos, cell[None], [n], 5.0, max_num_neighbors_threshold=k,
+                                                              enforce_max_neighbors_strictly=strict)
+            assert np.array_equal(ei.cpu().numpy(), oei), (n, k, strict)
+            assert np.array_equal(uc.cpu().numpy(), ouc)
+            assert np.array_equal(direc.cpu().numpy().view(np.uint32), odir.view(np.uint32))
+            deg = np.bincount(oei[1], minlength=n)
+            assert deg.min() >= min(k, 1) and (strict is False or deg.max() <= k)
