@@ -111,7 +111,7 @@ class DevicePrefetcher:
     reference's DataLoader(pin_memory=True) + `batch.to("cuda:0")` (/root/reference/loader/loader.py:114-124,
     train/train.py:169)."""
 
-    def __init__(self, batches, device, num_nodes_attr: str = "x"):
+    def __init__(self, batches, device):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)

@@ -1,4 +1,5 @@
-// Fused GEMM epilogue shared by the fp32 SIMT kernel and the tcgen05 kernel.
+// Fused GEMM epilogue: parameter block shared by the fp32 SIMT kernel and the tcgen05 kernel (whose compile-time
+// specialised epilogue lives in gemm_tc.cu) and the fp64 epilogue of the fp32 parity GEMM.
 // Order (see cartnet_gemm_t in include/cartnet_b200.h):
 //   v = acc + bias[col] + gather0[gidx0[row], col] + gather1[gidx1[row], col]
 //   z_out = v ; v = act(v, z_in) ; v += resid ; out_f32 = v ; out_t = (T) v
@@ -57,36 +58,6 @@ __device__ __forceinline__ EpiRow<T> epi_row(const EpiParams<T>& p, int64_t row)
     r.g0 = p.gather0 ? p.gather0 + (int64_t)p.gidx0[row] * p.ldg : nullptr;
     r.g1 = p.gather1 ? p.gather1 + (int64_t)p.gidx1[row] * p.ldg : nullptr;
     return r;
-}
-
-// 4 consecutive columns [col, col+4) of one row; col % 4 == 0 and all leading dimensions % 4 == 0
-template <typename T>
-__device__ __forceinline__ void epi_apply4(const EpiParams<T>& p, const EpiRow<T>& r, int64_t row, int col, float4 v) {
-    if (p.bias) {
-        float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
-    if (r.g0) {
-        float4 a = load4<T>(r.g0 + col);
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-    }
-    if (r.g1) {
-        float4 a = load4<T>(r.g1 + col);
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-    }
-    if (p.z_out) store4<T>(p.z_out + row * p.ldz + col, v);
-    if (p.act == CARTNET_ACT_SILU) {
-        v.x = siluf_(v.x); v.y = siluf_(v.y); v.z = siluf_(v.z); v.w = siluf_(v.w);
-    } else if (p.act == CARTNET_ACT_MUL_DSILU) {
-        float4 z = load4<T>(p.z_in + row * p.ldzin + col);
-        v.x *= dsiluf_(z.x); v.y *= dsiluf_(z.y); v.z *= dsiluf_(z.z); v.w *= dsiluf_(z.w);
-    }
-    if (p.resid) {
-        float4 a = *reinterpret_cast<const float4*>(p.resid + row * p.ldr + col);
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-    }
-    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + col) = v;
-    if (p.out_t) store4<T>(p.out_t + row * p.ldt + col, v);
 }
 
 // fp64 variant used by the fp32 parity GEMM: the accumulator arrives in double and bias / gathered projections /

@@ -49,11 +49,6 @@ def _req(t: torch.Tensor, dtype, name: str, rowmajor: bool = True):
     return t
 
 
-def _ld(t: torch.Tensor) -> int:
-    """leading dimension (elements) of a 2-D row-major view"""
-    return t.stride(0) if t.dim() == 2 and t.shape[0] > 1 else (t.shape[-1] if t.dim() == 2 else 0)
-
-
 def _ld2(t: torch.Tensor) -> int:
     if t.dim() != 2:
         raise ValueError("expected a 2-D tensor")

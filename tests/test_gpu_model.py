@@ -184,3 +184,29 @@ def test_graph_kernel_feeds_model_end_to_end():
         pr, _ = orc(batch_cpu.clone())
         pg, _ = model(b)
     assert common.rel_err(pg, pr) < 1e-5
+
+
+def test_graph_without_edges_eval():
+    """Isolated atoms (no pair within the radius): E = 0 flows through the graph build, the encoder and every layer in
+    eval mode; nodes without in-edges receive a zero message (cartnet.py:259-260) and only the BatchNorm shift survives."""
+    from cartnet_b200 import build_graph
+    from cartnet_b200.batch import CrystalBatch
+    pos = torch.tensor([[0.5, 0.5, 0.5], [10.0, 10.0, 10.0]], device="cuda")
+    cell = (torch.eye(3, device="cuda") * 20.0)[None]
+    gr = build_graph(pos, cell, torch.tensor([2], device="cuda"), 1.0)
+    assert gr["edge_index"].shape == (2, 0)
+    kw = dict(invariant=False, temperature=True, use_envelope=True, atom_types=True, cholesky=True)
+    model = cartnet_b200.CartNet(256, 64, 2, precision="fp32", **kw).cuda().eval()
+    orc = O.OracleCartNet(256, 64, 2, **kw)
+    orc.load_state_dict(model.state_dict())
+    orc.eval()
+    fields = dict(x=torch.tensor([6, 8]), batch=torch.zeros(2, dtype=torch.int64), natoms=torch.tensor([2]),
+                  temperature=torch.tensor([0.3]), non_H_mask=torch.tensor([True, True]), y=torch.zeros(2, 3, 3),
+                  edge_index=gr["edge_index"].cpu(), cart_dist=gr["cart_dist"].cpu(), cart_dir=gr["cart_dir"].cpu())
+    with torch.no_grad():
+        pr, _ = orc(CrystalBatch(**fields))
+        pg, _ = model(CrystalBatch(**fields).to("cuda"))
+    assert common.rel_err(pg, pr) < 1e-5
+    model.train()
+    with pytest.raises(ValueError):                       # BatchNorm over zero edges, like nn.BatchNorm1d
+        model(CrystalBatch(**fields).to("cuda"))
