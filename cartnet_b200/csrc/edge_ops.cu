@@ -517,6 +517,7 @@ int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, in
 int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const float* means, const float* betas,
                           int32_t num_rbf, float cutoff_upper, int32_t invariant, int64_t num_edges, void* feat,
                           int32_t ld, int32_t prec, cartnet_stream_t stream) {
+    if (num_edges <= 0) return 0;      // empty graph: zero-sized tensors carry null data pointers
     CN_CHECK_ARG(cart_dist && means && betas && feat, "edge_features: null pointer");
     CN_CHECK_ARG(invariant || cart_dir, "edge_features: cart_dir required unless invariant");
     CN_CHECK_ARG(ld % 4 == 0 && ld >= num_rbf + (invariant ? 0 : 3), "edge_features: ld=%d too small", ld);
@@ -660,6 +661,7 @@ int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const in
 
 int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy, int64_t rows,
                       int32_t C, int32_t prec, cartnet_stream_t stream) {
+    if (rows <= 0) return 0;
     CN_CHECK_ARG(dy && z && y && C % 4 == 0 && ld_dy % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "dsilu_mul: bad arguments");
     if (rows <= 0) return 0;
     const int64_t total = rows * (C / 4);
@@ -673,6 +675,7 @@ int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz
 
 int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C, int32_t prec,
                       cartnet_stream_t stream) {
+    if (rows <= 0) return 0;
     CN_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cast_rows: bad arguments");
     if (rows <= 0) return 0;
     const int64_t total = rows * (C / 4);

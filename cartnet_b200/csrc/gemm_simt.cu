@@ -164,6 +164,7 @@ extern "C" {
 int cartnet_gemm(const cartnet_gemm_t* d, cartnet_stream_t stream) {
     CN_CHECK_ARG(d, "gemm: null descriptor");
     CN_CHECK_ARG(d->M >= 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
+    if (d->M == 0) return 0;           // empty graph: zero-sized tensors carry null data pointers
     CN_CHECK_ARG(d->A && d->B, "gemm: null operand");
     CN_CHECK_ARG(d->N % 4 == 0 && d->K % 4 == 0 && d->lda % 4 == 0 && d->ldb % 4 == 0, "gemm: N,K,lda,ldb must be multiples of 4");
     CN_CHECK_ARG(!(d->act == CARTNET_ACT_MUL_DSILU) || d->z_in, "gemm: ACT_MUL_DSILU needs z_in");
