@@ -515,6 +515,19 @@ tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------ host
+// cudaFuncSetAttribute is per device: remember it per (kernel, device), not per process
+template <typename K>
+static int ensure_big_smem(K kernel, bool* done /* [64] */) {
+    int dev = 0;
+    CN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!done[dev]) {
+        CN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done[dev] = true;
+    }
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -582,11 +595,8 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     const EpiParams<T> epi = make_epi<T>(d);
 #define CN_NT_CASE(M_)                                                                                               \
     if (mask == (M_)) {                                                                                              \
-        static bool attr_done = false;                                                                               \
-        if (!attr_done) {                                                                                            \
-            CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T, (M_)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-            attr_done = true;                                                                                        \
-        }                                                                                                            \
+        static bool attr_done[64] = {};                                                                              \
+        if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_)>, attr_done)) return rc_;                                 \
         tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);   \
         CN_LAUNCH_CHECK();                                                                                           \
         return 0;                                                                                                    \
@@ -601,11 +611,8 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF)                     // edge encoder, second Linear (tf32)
 #undef CN_NT_CASE
     {
-        static bool attr_done = false;
-        if (!attr_done) {
-            CN_CUDA(cudaFuncSetAttribute(tc_nt_kernel<T, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
-        }
+        static bool attr_done[64] = {};
+        if (int rc_ = ensure_big_smem(tc_nt_kernel<T, EPI_GENERIC>, attr_done)) return rc_;
         tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);
         CN_LAUNCH_CHECK();
     }
@@ -659,11 +666,8 @@ static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda,
     const int box_bytes = TR::KB * 128;
     const size_t stage_bytes = (size_t)(TN_MBLK / TR::KB) * box_bytes + (size_t)(p.Nblk / TR::KB) * box_bytes;
     const size_t smem = 1024 + TN_STAGES * stage_bytes + sizeof(TnBars) + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CN_CUDA(cudaFuncSetAttribute(tc_tn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    static bool attr_done[64] = {};
+    if (int rc_ = ensure_big_smem(tc_tn_kernel<T>, attr_done)) return rc_;
     tc_tn_kernel<T><<<dim3(p.splits, p.m_blocks * p.n_blocks), TN_THREADS, smem, st>>>(
         tmA, tmB, K, M, N, p.Nblk, p.n_blocks, p.kblks_total, p.kblks_per_split, ws);
     CN_LAUNCH_CHECK();
