@@ -72,6 +72,11 @@ def graph_cases():
     cases["knn200_adp60"] = dict(pos=p, cell=c[None], natoms=[60], radius=5.0, knn=200)          # nothing exceeds -> all kept
     cases["knn6_cubic2"] = dict(pos=np.array([[0, 0, 0], [1.5, 1.5, 1.5]], np.float32),          # highly degenerate shells
                                 cell=(np.eye(3, dtype=np.float32) * 3.0)[None], natoms=[2], radius=5.0, knn=6)
+    # non-periodic axes (dataset/utils.py:141-156: rep = 0 along them) via the batch's own pbc field (:67-77)
+    p, c = synth(30, 9.5, 13)
+    cases["slab_pbc110"] = dict(pos=p, cell=c[None], natoms=[30], radius=5.0, pbc=[True, True, False])
+    cases["wire_pbc001"] = dict(pos=p, cell=c[None], natoms=[30], radius=5.0, pbc=[False, False, True])
+    cases["molecule_pbc000"] = dict(pos=p, cell=c[None], natoms=[30], radius=5.0, pbc=[False, False, False])
     p1, c1 = synth(12, 15.0, 5)
     p2, c2 = synth(33, 9.5, 6)
     cases["knn16_batch2"] = dict(pos=np.concatenate([p1, p2]), cell=np.stack([c1, c2]), natoms=[12, 33], radius=5.0, knn=16)
@@ -83,10 +88,11 @@ def run_graph(dutils):
     for name, cs in graph_cases().items():
         data = SimpleNamespace(pos=torch.from_numpy(cs["pos"]), cell=torch.from_numpy(cs["cell"]),
                                natoms=torch.tensor(cs["natoms"], dtype=torch.int64),
-                               pbc=torch.tensor([[True, True, True]]))
+                               pbc=torch.tensor([cs.get("pbc", [True, True, True])]))
         ei, uc, dist, direc = dutils.radius_graph_pbc(data, cs["radius"], cs.get("knn"), pbc=[True, True, True])
         ei, uc, dist, direc = ei.numpy(), uc.numpy(), dist.numpy(), direc.numpy()
         oei, ouc, odist, odir = O.radius_graph_pbc_oracle(cs["pos"], cs["cell"], cs["natoms"], cs["radius"],
+                                                          pbc=tuple(cs.get("pbc", [True, True, True])),
                                                           max_num_neighbors_threshold=cs.get("knn"))
         assert np.array_equal(ei, oei), name
         assert np.array_equal(uc, ouc), name
@@ -105,6 +111,7 @@ def run_graph(dutils):
         out[pre + "natoms"] = np.asarray(cs["natoms"], np.int64)
         out[pre + "radius"] = np.float64(cs["radius"])
         out[pre + "knn"] = np.int64(cs.get("knn") or 0)
+        out[pre + "pbc"] = np.asarray(cs.get("pbc", [True, True, True]), dtype=bool)
         out[pre + "num_edges"] = np.int64(ei.shape[1])
         out[pre + "sha_edge_index"] = sha(ei)
         out[pre + "sha_unit_cell"] = sha(uc)

@@ -12,18 +12,18 @@ from types import SimpleNamespace
 pytestmark = pytest.mark.gpu
 
 
-def _data(pos, cell, natoms):
+def _data(pos, cell, natoms, pbc=(True, True, True)):
     return SimpleNamespace(pos=torch.from_numpy(np.asarray(pos)).cuda(), cell=torch.from_numpy(np.asarray(cell)).cuda(),
                            natoms=torch.as_tensor(np.asarray(natoms), dtype=torch.int64).cuda(),
-                           pbc=torch.tensor([[True, True, True]]).cuda())
+                           pbc=torch.tensor([[bool(v) for v in pbc]]).cuda())
 
 
 def test_golden_graphs_bit_exact(golden_graph):
     g = golden_graph
     for name in common.graph_case_names(g):
         pre = name + "/"
-        ei, uc, dist, direc = radius_graph_pbc(_data(g[pre + "pos"], g[pre + "cell"], g[pre + "natoms"]),
-                                               float(g[pre + "radius"]), int(g[pre + "knn"]) or None)
+        ei, uc, dist, direc = radius_graph_pbc(_data(g[pre + "pos"], g[pre + "cell"], g[pre + "natoms"], g[pre + "pbc"]),
+                                               float(g[pre + "radius"]), int(g[pre + "knn"]) or None, pbc=[True, True, True])
         ei, uc, dist, direc = ei.cpu().numpy(), uc.cpu().numpy(), dist.cpu().numpy(), direc.cpu().numpy()
         assert ei.shape[1] == int(g[pre + "num_edges"]), name
         assert common.sha(ei) == str(g[pre + "sha_edge_index"]), name

@@ -210,3 +210,31 @@ def test_graph_without_edges_eval():
     model.train()
     with pytest.raises(ValueError):                       # BatchNorm over zero edges, like nn.BatchNorm1d
         model(CrystalBatch(**fields).to("cuda"))
+
+
+@pytest.mark.parametrize("temperature,atom_types", [(True, True), (False, True), (True, False), (False, False)])
+@pytest.mark.parametrize("cholesky", [True, False])
+def test_encoder_variants_match_oracle(temperature, atom_types, cholesky):
+    """All four node-encoder variants of Encoder.forward (cartnet.py:144-154: embedding+temperature, embedding+bias,
+    temperature only, single learned vector) with both heads, training step against the oracle (fp32 mode)."""
+    seed = 51
+    batch = fixtures.make_oracle_batch("mp", 5, seed, cholesky=cholesky, temperature=True)
+    if not cholesky:
+        batch.y = batch.y.reshape(-1)
+    kw = dict(invariant=False, temperature=temperature, use_envelope=True, atom_types=atom_types, cholesky=cholesky)
+    torch.manual_seed(0)
+    orc = O.OracleCartNet(256, 64, 2, **kw)
+    sd = fixtures.make_state_dict(orc.state_dict(), seed)
+    orc.load_state_dict(sd)
+    model = cartnet_b200.CartNet(256, 64, 2, precision="fp32", **kw)
+    model.load_state_dict(sd)
+    model.cuda()
+    ref = common.run_train_step(orc, batch)
+    got = common.run_train_step(model, batch.clone().to("cuda"))
+    assert common.rel_err(got["pred"], ref["pred"]) < 1e-5
+    assert common.rel_err(got["pred_eval"], ref["pred_eval"]) < 1e-5
+    scale = max(float(v.abs().max()) for v in ref["grads"].values())
+    for k, g in ref["grads"].items():
+        if k.endswith("MLP_gate.2.bias"):
+            continue                                  # analytically zero gradient (see tests/test_gpu_configs.py)
+        assert float((got["grads"][k].cpu() - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-5 * scale, k

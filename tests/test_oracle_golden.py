@@ -24,7 +24,7 @@ def test_graph_oracle_matches_reference(golden_graph):
     for name in names:
         pre = name + "/"
         ei, uc, dist, direc = O.radius_graph_pbc_oracle(g[pre + "pos"], g[pre + "cell"], g[pre + "natoms"],
-                                                        float(g[pre + "radius"]),
+                                                        float(g[pre + "radius"]), pbc=tuple(bool(v) for v in g[pre + "pbc"]),
                                                         max_num_neighbors_threshold=int(g[pre + "knn"]) or None)
         assert ei.shape[1] == int(g[pre + "num_edges"]), name
         assert common.sha(ei) == str(g[pre + "sha_edge_index"]), name          # bit-exact: edge set and order
