@@ -252,7 +252,7 @@ struct EdgeBwdF {
         const int64_t o = r * D + col;
         in.g = __ldg(reinterpret_cast<const float4*>(g + o));
         in.s = __ldg(reinterpret_cast<const float4*>(s + o));
-        in.de = __ldg(reinterpret_cast<const float4*>(de + o));
+        in.de = de ? __ldg(reinterpret_cast<const float4*>(de + o)) : make_float4(0.f, 0.f, 0.f, 0.f);   // null = no gradient into e_out
         in.dmd = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)__ldg(dst + r) * D + col));
         in.dist = use_env ? __ldg(dist + r) : 0.f;
     }
@@ -610,7 +610,7 @@ int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* di
                                  const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
                                  float eps, float radius, int32_t use_envelope, void* ds_t, float* dghat, int32_t prec,
                                  float* sums, double* partial, cartnet_stream_t stream) {
-    CN_CHECK_ARG(g && s && dist && dst32 && de_out && dm && bn_mean && bn_var && ds_t && dghat && sums && partial &&
+    CN_CHECK_ARG(g && s && dist && dst32 && dm && bn_mean && bn_var && ds_t && dghat && sums && partial &&
                      num_edges > 0, "edge_gate_bwd_reduce: bad arguments");
     CN_CHECK_ARG(colreduce_shape_ok(D), "edge_gate_bwd_reduce: unsupported D=%d", D);
     cudaStream_t st = (cudaStream_t)stream;

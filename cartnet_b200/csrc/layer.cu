@@ -146,7 +146,7 @@ int cartnet_layer_fwd(const cartnet_layer_t* L, cartnet_stream_t st) {
 }
 
 int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
-    CN_CHECK_ARG(L && L->dx_out && L->de_out, "layer_bwd: null gradient input");
+    CN_CHECK_ARG(L && L->dx_out, "layer_bwd: null gradient input");      // de_out may be null (= zero)
     const int D = L->D, N = L->num_nodes, prec = L->prec;
     const int64_t E = L->num_edges;
     const float *mean1 = L->training ? L->mean1 : L->bn1_rm, *var1 = L->training ? L->var1 : L->bn1_rv;
@@ -176,7 +176,7 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     // first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
     {
         cartnet_gemm_t d = gemm_desc(prec, (int)E, D, 2 * D, L->dZ, 2 * D, L->W1eT_t, 2 * D);
-        d.resid = L->de_out; d.ldr = D; d.out_f32 = L->de_in; d.ldo = D;
+        d.resid = L->de_out; d.ldr = D; d.out_f32 = L->de_in; d.ldo = D;      // null resid: plain store
         CN_TRY(cartnet_gemm(&d, st));
     }
     // d(W_e) = dZ^T e, written block-wise into the reference layout dG1[:, 2D:3D], dA1[:, 2D:3D]

@@ -265,6 +265,7 @@ class _NativeLayerFn(torch.autograd.Function):
         _lib.check(lib.cartnet_layer_fwd(C.byref(L), st), "layer_fwd")
         cfg["holder"]["x_t"] = x_out_t if shadow else x_out
         cfg["holder"]["e_t"] = e_out_t if shadow else e_out
+        ctx.set_materialize_grads(False)     # an unused edge_attr output arrives as None in backward, not as zeros
         ctx.L = L
         ctx.keep = (x, e, x_t, e_t, tbuf, fbuf, dist, plan, cfg["rm1"], cfg["rv1"], cfg["rm2"], cfg["rv2"]) + tuple(
             v.detach() for v in params.values())
@@ -281,7 +282,7 @@ class _NativeLayerFn(torch.autograd.Function):
         T = t_dtype(prec)
         dev = ctx.keep[0].device
         dx_out = torch.zeros(N, D, dtype=torch.float32, device=dev) if dx_out is None else dx_out.contiguous()
-        de_out = torch.zeros(E, D, dtype=torch.float32, device=dev) if de_out is None else de_out.contiguous()
+        de_out = None if de_out is None else de_out.contiguous()      # None: no gradient into e_out (last layer)
         tbuf = torch.empty(2 * E * D + E * 2 * D + N * 4 * D, dtype=T, device=dev)
         ds_t, dg_t, dZ, dP = _carve(tbuf, [(E, D), (E, D), (E, 2 * D), (N, 4 * D)])
         fbuf = torch.empty(N * D + E * D + 5 * D, dtype=torch.float32, device=dev)

@@ -207,7 +207,8 @@ int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t n
 
 /* Backward edge pass, step 1 (per edge, channel):  dmd = dm[dst];  ds = sig * dmd  -> ds_t (T);
  * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat (fp32);
- * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm, sums[2D:3D] = sum_e ds (sums has 3D entries). */
+ * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm, sums[2D:3D] = sum_e ds (sums has 3D entries).
+ * de_out may be null (no gradient flows into e_out, e.g. the last layer: the heads read only x). */
 int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
                                  const float* bn_mean, const float* bn_var, const float* bn_weight,
@@ -268,7 +269,7 @@ typedef struct cartnet_layer {
     float *x_out, *e_out;                            /* [N,D], [E,D] */
     void *x_out_t, *e_out_t;                         /* T copies for the next layer (null when T = float) */
     /* backward: inputs, scratch, outputs */
-    const float *dx_out, *de_out;
+    const float *dx_out, *de_out;                    /* de_out may be null: treated as zero without being read */
     float* dm;                                       /* [N,D] */
     void *ds_t, *dg_t;                               /* T [E,D] */
     float* dghat;                                    /* [E,D] */
