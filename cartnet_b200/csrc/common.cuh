@@ -47,6 +47,16 @@ __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- operand type helpers -------------------------------------------------------------
+// Storage type of the TF32 tensor-core mode: an fp32 word whose STORES round to nearest tf32 (10-bit mantissa,
+// cvt.rna). tcgen05 kind::tf32 simply ignores the low 13 mantissa bits, i.e. truncates; rounding where the operand
+// is produced removes that bias. Loads are plain fp32 loads.
+struct tf32_t { float v; };
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -54,8 +64,13 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+template <>
+__device__ __forceinline__ float to_f32<tf32_t>(tf32_t v) { return v.v; }
+
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ tf32_t from_f32<tf32_t>(float v) { tf32_t t; t.v = round_tf32(v); return t; }
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
@@ -74,8 +89,14 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
     float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
     return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+template <>
+__device__ __forceinline__ float4 load4<tf32_t>(const tf32_t* p) { return *reinterpret_cast<const float4*>(p); }
 template <typename T>
 __device__ __forceinline__ void store4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<tf32_t>(tf32_t* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
 template <>
 __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 template <>
@@ -111,7 +132,7 @@ __device__ __forceinline__ float cosine_cutoff(float d, float upper) {
             using T = __nv_bfloat16;                                        \
             __VA_ARGS__                                                     \
         } else if ((prec) == CARTNET_PREC_TF32) {                           \
-            using T = float;                                                \
+            using T = cartnet::tf32_t;                                      \
             __VA_ARGS__                                                     \
         } else {                                                            \
             cartnet::set_error("unknown prec %d", (int)(prec));             \

@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / TMA GEMMs for sm_100a (CARTNET_PREC_BF16: kind::f16 on bf16 operands,
-// CARTNET_PREC_TF32: kind::tf32 reading the fp32 tensors directly). Hand-written PTX; descriptor bit
+// CARTNET_PREC_TF32: kind::tf32 on fp32 words that were rounded to tf32 where they were produced). Hand-written PTX; descriptor bit
 // layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 //
 // NT kernel  C[M,N] = A[M,K] B[N,K]^T  (+ fused epilogue, gemm_epilogue.cuh)
@@ -137,7 +137,7 @@ struct TcTraits<__nv_bfloat16> {
     static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B;
 };
 template <>
-struct TcTraits<float> {
+struct TcTraits<tf32_t> {
     static constexpr int KB = 32;
     static constexpr int UMMA_K = 8;
     static constexpr int FMT = 2;
@@ -177,10 +177,10 @@ __host__ __device__ constexpr bool epi_has(int bit, bool runtime) { return EPI =
 
 // raw (unconverted) 4-element loads so that all global reads of a chunk can be issued before any math / store
 template <typename T> struct Raw4;
-template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<tf32_t> { using type = float4; };
 template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
 template <typename T> __device__ __forceinline__ typename Raw4<T>::type ld_raw4(const T* p);
-template <> __device__ __forceinline__ float4 ld_raw4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 ld_raw4<tf32_t>(const tf32_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 template <> __device__ __forceinline__ uint2 ld_raw4<__nv_bfloat16>(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ float4 cvt_raw4(const float4& r) { return r; }
 __device__ __forceinline__ float4 cvt_raw4(const uint2& r) {
@@ -622,7 +622,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
 
 int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     if (d.prec == CARTNET_PREC_BF16) return run_nt<__nv_bfloat16>(d, st);
-    return run_nt<float>(d, st);
+    return run_nt<tf32_t>(d, st);
 }
 
 struct TnPlan {
@@ -682,7 +682,7 @@ int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, co
         return 0;
     }
     if (prec == CARTNET_PREC_BF16) return run_tn<__nv_bfloat16>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
-    return run_tn<float>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
+    return run_tn<tf32_t>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
 }
 
 }  // namespace cartnet

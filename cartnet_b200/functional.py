@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32, f32_storage, t_dtype
+from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype
 
 
 def _round_up(v: int, m: int) -> int:
@@ -27,6 +27,8 @@ def _round_up(v: int, m: int) -> int:
 def _to_t(w: torch.Tensor, prec: int) -> torch.Tensor:
     """weights are tiny (<= 1 MB): a torch cast is plumbing, not hot path"""
     w = w.detach()
+    if prec == PREC_TF32:
+        return ops.cast(w.contiguous(), prec)          # fp32 words rounded to tf32 (the MMA would truncate otherwise)
     return w.contiguous() if f32_storage(prec) else w.to(torch.bfloat16).contiguous()
 
 
@@ -47,9 +49,9 @@ class _EdgeEncoderFn(torch.autograd.Function):
         ops.gemm(prec, feat, Wa_t, bias=ba.detach(), z_out=Z1, act=ACT_SILU, out_t=H1)
         Z2 = torch.empty(E, D, dtype=T, device=dev)
         e0 = torch.empty(E, D, dtype=torch.float32, device=dev)
-        e0_t = None if f32_storage(prec) else torch.empty(E, D, dtype=T, device=dev)
+        e0_t = torch.empty(E, D, dtype=T, device=dev) if needs_shadow(prec) else None
         ops.gemm(prec, H1, Wb_t, bias=bb.detach(), z_out=Z2, act=ACT_SILU, out_f32=e0, out_t=e0_t)
-        holder["e_t"] = e0 if f32_storage(prec) else e0_t
+        holder["e_t"] = e0_t if needs_shadow(prec) else e0
         ctx.save_for_backward(feat, Z1, H1, Z2, Wb)
         ctx.prec, ctx.dim_edge = prec, dim_edge
         return e0
@@ -233,7 +235,7 @@ class _NativeLayerFn(torch.autograd.Function):
             x_t = ops.cast(x, prec)
         if e_t is None:
             e_t = ops.cast(e, prec)
-        shadow = not f32_storage(prec)
+        shadow = needs_shadow(prec)
         DD = D * D
         tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D, dtype=T, device=dev)
         (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H) = _carve(tbuf, [

@@ -24,7 +24,14 @@ def t_dtype(prec: int) -> torch.dtype:
 
 
 def f32_storage(prec: int) -> bool:
+    """dtype of T-typed buffers is torch.float32 (fp32 and tf32 modes)"""
     return prec != PREC_BF16
+
+
+def needs_shadow(prec: int) -> bool:
+    """the tensor-core modes keep separate T-typed operand copies of x / e (bf16, or fp32 words rounded to tf32);
+    in fp32 mode the fp32 tensors themselves are the operands"""
+    return prec != PREC_FP32
 
 
 def launch_count() -> int:
@@ -294,13 +301,13 @@ def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes: int, bn_mean, bn_var,
             raise ValueError("%s must be contiguous" % nm)
     E, D = int(e.shape[0]), int(e.shape[1])
     e_out = torch.empty_like(e)
-    e_out_t = torch.empty(E, D, dtype=t_dtype(prec), device=e.device) if (want_shadow and not f32_storage(prec)) else None
+    e_out_t = torch.empty(E, D, dtype=t_dtype(prec), device=e.device) if (want_shadow and needs_shadow(prec)) else None
     m = torch.empty(num_nodes, D, dtype=torch.float32, device=e.device)
     _lib.check(lib.cartnet_edge_gate_aggregate(
         _p(g), _p(s), _p(e), _p(dist), _p(row_ptr), num_nodes, E, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b),
         EPS_BN, float(radius), int(bool(use_envelope)), _p(e_out), _p(e_out_t), prec, _p(m), _stream()),
         "edge_gate_aggregate")
-    return e_out, (e_out_t if e_out_t is not None else (e_out if f32_storage(prec) else None)), m
+    return e_out, (e_out_t if e_out_t is not None else (e_out if not needs_shadow(prec) else None)), m
 
 
 def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec: int, want_shadow: bool):
@@ -309,10 +316,10 @@ def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec: int, want_shadow: bool)
     x = x.contiguous()
     N, D = int(x.shape[0]), int(x.shape[1])
     x_out = torch.empty_like(x)
-    x_out_t = torch.empty(N, D, dtype=t_dtype(prec), device=x.device) if (want_shadow and not f32_storage(prec)) else None
+    x_out_t = torch.empty(N, D, dtype=t_dtype(prec), device=x.device) if (want_shadow and needs_shadow(prec)) else None
     _lib.check(lib.cartnet_node_update(_p(m), _p(x), N, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b), EPS_BN,
                                        _p(x_out), _p(x_out_t), prec, _stream()), "node_update")
-    return x_out, (x_out_t if x_out_t is not None else (x_out if f32_storage(prec) else None))
+    return x_out, (x_out_t if x_out_t is not None else (x_out if not needs_shadow(prec) else None))
 
 
 def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training: bool):
@@ -374,8 +381,8 @@ def dsilu_mul(dy, z, prec: int) -> torch.Tensor:
 
 
 def cast(x, prec: int) -> torch.Tensor:
-    """fp32 -> T operand copy (identity object for the fp32 path)."""
-    if f32_storage(prec):
+    """fp32 -> T operand copy: bf16, or fp32 rounded to tf32; the identity object in fp32 mode."""
+    if not needs_shadow(prec):
         return x
     lib = _lib.load()
     _req(x, torch.float32, "x")

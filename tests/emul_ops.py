@@ -15,7 +15,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_FP32, GraphPlan, f32_storage, t_dtype  # noqa: F401
+from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_FP32, PREC_TF32, GraphPlan, f32_storage, needs_shadow, t_dtype  # noqa: F401
 
 EPS_BN = 1e-5
 
@@ -25,6 +25,18 @@ def _f(t):
 
 
 HIGH = False   # set True to emulate in fp64 (tolerance budgeting)
+
+
+def _rna_tf32(t):
+    """fp32 -> nearest tf32 (ties away), like cvt.rna.tf32.f32"""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+def _shadow(t, prec):
+    if not needs_shadow(prec):
+        return t
+    return _rna_tf32(t) if prec == PREC_TF32 else t.to(t_dtype(prec))
 
 
 def _dsilu(z):
@@ -127,14 +139,14 @@ def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes, bn_mean, bn_var, bn_w
     counts = (row_ptr[1:] - row_ptr[:-1]).long()
     dst = torch.repeat_interleave(torch.arange(num_nodes), counts)
     m = torch.zeros(num_nodes, e.shape[1], dtype=sig.dtype).index_add_(0, dst, sig * _f(s)).float()
-    e_t = e_out if f32_storage(prec) else e_out.to(t_dtype(prec))
+    e_t = _shadow(e_out, prec)
     return e_out, e_t, m
 
 
 def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec, want_shadow):
     y, _, _ = _bn(_f(m), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
     x_out = (F.silu(y) + _f(x)).float()
-    return x_out, (x_out if f32_storage(prec) else x_out.to(t_dtype(prec)))
+    return x_out, _shadow(x_out, prec)
 
 
 def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training):
@@ -176,7 +188,7 @@ def dsilu_mul(dy, z, prec):
 
 
 def cast(x, prec):
-    return x if f32_storage(prec) else x.to(t_dtype(prec))
+    return _shadow(x, prec)
 
 
 ALL = ["graph_plan", "edge_features", "gemm", "gemm_tn", "colstats", "colsum", "edge_gate_aggregate", "node_update",

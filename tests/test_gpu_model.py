@@ -238,3 +238,16 @@ def test_encoder_variants_match_oracle(temperature, atom_types, cholesky):
         if k.endswith("MLP_gate.2.bias"):
             continue                                  # analytically zero gradient (see tests/test_gpu_configs.py)
         assert float((got["grads"][k].cpu() - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-5 * scale, k
+
+
+@pytest.mark.parametrize("name", list(common.MODEL_CASES))
+def test_tf32_mode_eval_within_2e3_on_every_golden_case(golden_model, name):
+    """north_star: "the bf16/TF32 tensor-core path within 2e-3 relative". The tf32 mode (operands rounded to nearest tf32
+    where they are produced, fp32 accumulation in TMEM) holds that in eval mode on every reference golden case."""
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
+    batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes), cholesky=kw["cholesky"],
+                                        temperature=kw["temperature"]).to("cuda")
+    model = _model(kw, seed, lrad, "tf32").eval()
+    with torch.no_grad():
+        pred, _ = model(batch0.clone())
+    assert common.rel_err(pred, torch.from_numpy(golden_model[name + "/pred_eval"])) < 2e-3
