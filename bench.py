@@ -218,10 +218,11 @@ class OpTimer:
                 nbytes = es(A) + es(B)
             elif name == "edge_gate_aggregate":
                 g = a[0]
-                nbytes = 4.0 * g.numel() * 4 + (2.0 * g.numel() if a[12] == 1 else 0)     # g,s,e read + e' write (+bf16 shadow)
+                ts = a[1].element_size()
+                nbytes = g.numel() * (4.0 * 3 + 2 * ts + (ts if a[12] != 0 else 0))      # g,e read, e' write (fp32); s read, gn write (T) (+T shadow)
             elif name == "edge_gate_bwd":
                 g = a[0]
-                nbytes = 4.0 * g.numel() * (3 + 2) + 2 * g.numel() * (2 if a[13] == 1 else 4)   # g,s,de read; dghat w+r; ds,dg write
+                nbytes = g.numel() * (4.0 + 7 * g.element_size())   # de read (fp32); gn x2, s, dghat r+w, ds, dg (T)
             elif name == "segment_sum":
                 nbytes = es(a[0])
             elif name in ("colstats", "colsum"):

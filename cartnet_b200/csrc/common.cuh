@@ -43,6 +43,12 @@ void count_launch();
 
 constexpr int kNumSMs = 148;  // B200
 
+// destination of a split-K weight gradient: up to 4 equal row blocks, each with its own base pointer
+struct TnDst {
+    float* c[4];
+    int rows_per_blk;
+};
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -91,6 +97,21 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
 }
 template <>
 __device__ __forceinline__ float4 load4<tf32_t>(const tf32_t* p) { return *reinterpret_cast<const float4*>(p); }
+// read-only (non-coherent) variants: the compiler may hoist them above unrelated stores
+template <typename T>
+__device__ __forceinline__ float4 ldg4(const T* p);
+template <>
+__device__ __forceinline__ float4 ldg4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 ldg4<tf32_t>(const tf32_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 ldg4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
 template <typename T>
 __device__ __forceinline__ void store4(T* p, float4 v);
 template <>

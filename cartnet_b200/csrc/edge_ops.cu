@@ -237,21 +237,28 @@ template <bool FAST> __device__ __forceinline__ float cutoff_sel(float d, float 
     if (FAST) return d < upper ? 0.5f * (__cosf(d * 3.14159265358979323846f / upper) + 1.0f) : 0.0f;
     return cosine_cutoff(d, upper);
 }
+// Inputs are the T-typed tensors the forward pass saved: gn = (g - mean) * rstd (the normalised gate pre-activation,
+// so no statistics are needed here) and s; the affine + sigmoid is recomputed in registers.
 template <typename T, bool FAST>
 struct EdgeBwdF {
-    static constexpr int NV = 3;      // sum dghat | sum dghat*ghat_norm | sum ds  (the last one is d(bias) of MLP_aggr[2])
+    static constexpr int NV = 3;      // sum dghat | sum dghat*gn | sum ds  (the last one is d(bias) of MLP_aggr[2])
     static constexpr bool F32_PARTIAL = true;
-    using State = BnCoef;
-    struct In { float4 g, s, de, dmd; float dist; };
-    const float *g, *s, *dist; const int32_t* dst; const float *de, *dm; int D;
-    const float *mean, *var, *w, *bias; float eps, radius; int use_env;
-    T* ds_t; float* dghat;
-    __device__ State init(int col) const { return bn_coef(mean, var, w, bias, eps, col); }
+    struct State { float4 w, b; };
+    struct In { float4 gn, s, de, dmd; float dist; };
+    const T *gn, *s; const float* dist; const int32_t* dst; const float *de, *dm; int D;
+    const float *w, *bias; float radius; int use_env;
+    T *ds_t, *dghat_t;
+    __device__ State init(int col) const {
+        State c;
+        c.w = w ? *reinterpret_cast<const float4*>(w + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+        c.b = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return c;
+    }
     __device__ void load(int64_t r, int col, In& in) const {
         // read-only (non-coherent) loads of U rows are all in flight before the first store
         const int64_t o = r * D + col;
-        in.g = __ldg(reinterpret_cast<const float4*>(g + o));
-        in.s = __ldg(reinterpret_cast<const float4*>(s + o));
+        in.gn = ldg4<T>(gn + o);
+        in.s = ldg4<T>(s + o);
         in.de = de ? __ldg(reinterpret_cast<const float4*>(de + o)) : make_float4(0.f, 0.f, 0.f, 0.f);   // null = no gradient into e_out
         in.dmd = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)__ldg(dst + r) * D + col));
         in.dist = use_env ? __ldg(dist + r) : 0.f;
@@ -259,8 +266,8 @@ struct EdgeBwdF {
     __device__ void compute(const State& c, int64_t r, int col, const In& in, float4* out) const {
         const float env = use_env ? cutoff_sel<FAST>(in.dist, radius) : 1.0f;
         const int64_t o = r * D + col;
-        const float4 gh = bn_apply(c, in.g), hn = bn_hat(c, in.g);
-        const float sg[4] = {sigmoid_sel<FAST>(gh.x), sigmoid_sel<FAST>(gh.y), sigmoid_sel<FAST>(gh.z), sigmoid_sel<FAST>(gh.w)};
+        const float sg[4] = {sigmoid_sel<FAST>(fmaf(in.gn.x, c.w.x, c.b.x)), sigmoid_sel<FAST>(fmaf(in.gn.y, c.w.y, c.b.y)),
+                             sigmoid_sel<FAST>(fmaf(in.gn.z, c.w.z, c.b.z)), sigmoid_sel<FAST>(fmaf(in.gn.w, c.w.w, c.b.w))};
         // ds = sig * dm[dst] ; dsig = de_out + s * dm[dst] ; dghat = dsig * env * sg (1 - sg)
         const float4 ds = make_float4(env * sg[0] * in.dmd.x, env * sg[1] * in.dmd.y, env * sg[2] * in.dmd.z, env * sg[3] * in.dmd.w);
         store4<T>(ds_t + o, ds);
@@ -268,9 +275,9 @@ struct EdgeBwdF {
                                      (in.de.y + in.s.y * in.dmd.y) * env * sg[1] * (1.f - sg[1]),
                                      (in.de.z + in.s.z * in.dmd.z) * env * sg[2] * (1.f - sg[2]),
                                      (in.de.w + in.s.w * in.dmd.w) * env * sg[3] * (1.f - sg[3]));
-        *reinterpret_cast<float4*>(dghat + o) = a;
+        store4<T>(dghat_t + o, a);
         out[0] = a;
-        out[1] = make_float4(a.x * hn.x, a.y * hn.y, a.z * hn.z, a.w * hn.w);
+        out[1] = make_float4(a.x * in.gn.x, a.y * in.gn.y, a.z * in.gn.z, a.w * in.gn.w);
         out[2] = ds;
     }
 };
@@ -293,21 +300,21 @@ template <> __device__ __forceinline__ double cutoff_r<double>(float d, float up
 
 template <typename T, typename R>
 __global__ void __launch_bounds__(256)
-edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict__ s, const float* __restrict__ e,
+edge_gate_aggregate_kernel(const float* __restrict__ g, const T* __restrict__ s, const float* __restrict__ e,
                            const float* __restrict__ dist, const int32_t* __restrict__ row_ptr, int num_nodes, int D,
                            const float* mean, const float* var, const float* w, const float* bias, float eps,
                            float radius, int use_env, float* __restrict__ e_out, T* __restrict__ e_out_t,
-                           float* __restrict__ m) {
+                           T* __restrict__ gn_t, float* __restrict__ m) {
     const int tpr = D >> 2, npb = 256 / tpr;
     const int node = blockIdx.x * npb + threadIdx.x / tpr;
     const int col = (threadIdx.x % tpr) * 4;
     if (node >= num_nodes) return;
-    R mu[4], sc[4], sh[4];
+    R mu[4], rs[4], sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         mu[j] = (R)mean[col + j];
-        const R rstd = (R)1 / sqrt((R)var[col + j] + (R)eps);
-        sc[j] = (w ? (R)w[col + j] : (R)1) * rstd;
+        rs[j] = (R)1 / sqrt((R)var[col + j] + (R)eps);
+        sc[j] = (w ? (R)w[col + j] : (R)1) * rs[j];
         sh[j] = bias ? (R)bias[col + j] : (R)0;
     }
     R acc[4] = {0, 0, 0, 0};
@@ -315,14 +322,16 @@ edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict_
     for (int k = k0; k < k1; ++k) {
         const int64_t o = (int64_t)k * D + col;
         const float4 g4 = *reinterpret_cast<const float4*>(g + o);
-        const float4 s4 = *reinterpret_cast<const float4*>(s + o);
+        const float4 s4 = load4<T>(s + o);
         const float4 e4 = *reinterpret_cast<const float4*>(e + o);
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
         const R env = use_env ? cutoff_r<R>(dist[k], radius) : (R)1;
-        float eo[4];
+        float eo[4], gn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const R gh = ((R)gg[j] - mu[j]) * sc[j] + sh[j];
+            const R gc = (R)gg[j] - mu[j];
+            gn[j] = (float)(gc * rs[j]);                            // normalised pre-activation, saved for backward
+            const R gh = gc * sc[j] + sh[j];
             const float sig = (float)(env * sigmoid_r<R>(gh));     // the reference materialises sigma_ij in fp32
             eo[j] = ee[j] + sig;                                    // cartnet.py:225
             acc[j] += (R)sig * (R)ss[j];                            // cartnet.py:259
@@ -330,6 +339,7 @@ edge_gate_aggregate_kernel(const float* __restrict__ g, const float* __restrict_
         const float4 eo4 = make_float4(eo[0], eo[1], eo[2], eo[3]);
         *reinterpret_cast<float4*>(e_out + o) = eo4;
         if (e_out_t) store4<T>(e_out_t + o, eo4);
+        if (gn_t) store4<T>(gn_t + o, make_float4(gn[0], gn[1], gn[2], gn[3]));
     }
     *reinterpret_cast<float4*>(m + (int64_t)node * D + col) = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
 }
@@ -382,27 +392,46 @@ __global__ void node_bwd_apply_kernel(const float* __restrict__ dx, const float*
     *reinterpret_cast<float4*>(dm + o) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// dg = w * rstd * (dghat - [train](sum1/E + gn * sum2/E)). Each thread owns 4 fixed columns (coefficients hoisted)
+// and walks rows with a grid stride, 4 rows of loads in flight.
 template <typename T>
-__global__ void edge_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ dghat, int64_t total4,
-                                      int D, int64_t num_edges, const float* mean, const float* var, const float* w,
-                                      float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total4) return;
-    const int64_t o = i * 4;
-    const int col = (int)(o % D);
-    const BnCoef c = bn_coef(mean, var, w, nullptr, eps, col);
-    const float4 h = bn_hat(c, *reinterpret_cast<const float4*>(g + o));
-    const float4 d = *reinterpret_cast<const float4*>(dghat + o);
-    const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
-    const float sc[4] = {c.scale.x, c.scale.y, c.scale.z, c.scale.w};
-    const float inv_n = 1.0f / (float)num_edges;
-    float out[4];
+__global__ void __launch_bounds__(256)
+edge_bwd_apply_kernel(const T* __restrict__ gn, const T* __restrict__ dghat, int64_t rows, int D, const float* var,
+                      const float* w, float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t) {
+    constexpr int U = 4;
+    const int tpr = D >> 2, lanes = 256 / tpr;
+    const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * 4;
+    float sc[4], c1[4], c2[4];
+    const float inv_n = 1.0f / (float)rows;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float corr = training ? (sums[col + j] * inv_n + hh[j] * sums[D + col + j] * inv_n) : 0.f;
-        out[j] = sc[j] * (dd[j] - corr);
+        sc[j] = (w ? w[col + j] : 1.0f) * (1.0f / sqrtf(var[col + j] + eps));
+        c1[j] = training ? sums[col + j] * inv_n : 0.f;
+        c2[j] = training ? sums[D + col + j] * inv_n : 0.f;
     }
-    store4<T>(dg_t + o, make_float4(out[0], out[1], out[2], out[3]));
+    const int64_t stride = (int64_t)gridDim.x * lanes;
+    int64_t r = (int64_t)blockIdx.x * lanes + rl;
+    for (; r + (U - 1) * stride < rows; r += U * stride) {
+        float4 h[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t o = (r + u * stride) * D + col;
+            h[u] = ldg4<T>(gn + o);
+            d[u] = ldg4<T>(dghat + o);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t o = (r + u * stride) * D + col;
+            store4<T>(dg_t + o, make_float4(sc[0] * (d[u].x - (c1[0] + h[u].x * c2[0])), sc[1] * (d[u].y - (c1[1] + h[u].y * c2[1])),
+                                            sc[2] * (d[u].z - (c1[2] + h[u].z * c2[2])), sc[3] * (d[u].w - (c1[3] + h[u].w * c2[3]))));
+        }
+    }
+    for (; r < rows; r += stride) {
+        const int64_t o = r * D + col;
+        const float4 h = ldg4<T>(gn + o), d = ldg4<T>(dghat + o);
+        store4<T>(dg_t + o, make_float4(sc[0] * (d.x - (c1[0] + h.x * c2[0])), sc[1] * (d.y - (c1[1] + h.y * c2[1])),
+                                        sc[2] * (d.z - (c1[2] + h.z * c2[2])), sc[3] * (d.w - (c1[3] + h.w * c2[3]))));
+    }
 }
 
 // out[n, :] = sum_{k in CSR row n} x[perm ? perm[k] : k, :]
@@ -536,25 +565,25 @@ int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const f
     return 0;
 }
 
-int cartnet_edge_gate_aggregate(const float* g, const float* s, const float* e, const float* dist,
+int cartnet_edge_gate_aggregate(const float* g, const void* s_t, const float* e, const float* dist,
                                 const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
                                 const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
-                                float eps, float radius, int32_t use_envelope, float* e_out, void* e_out_t, int32_t prec,
-                                float* m, cartnet_stream_t stream) {
+                                float eps, float radius, int32_t use_envelope, float* e_out, void* e_out_t, void* gn_t,
+                                int32_t prec, float* m, cartnet_stream_t stream) {
     CN_CHECK_ARG(row_ptr && bn_mean && bn_var && m, "edge_gate_aggregate: null pointer");
-    CN_CHECK_ARG(num_edges == 0 || (g && s && e && dist && e_out), "edge_gate_aggregate: null edge tensor");
+    CN_CHECK_ARG(num_edges == 0 || (g && s_t && e && dist && e_out), "edge_gate_aggregate: null edge tensor");
     CN_CHECK_ARG(row_shape_ok(D), "edge_gate_aggregate: unsupported D=%d", D);
     if (num_nodes <= 0) return 0;
     const int npb = 256 / (D / 4);
     if (prec == CARTNET_PREC_FP32) {
         edge_gate_aggregate_kernel<float, double><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
-            g, s, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope, e_out,
-            (float*)e_out_t, m);
+            g, (const float*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+            e_out, (float*)e_out_t, (float*)gn_t, m);
     } else {
         CN_DISPATCH_PREC(prec, {
             edge_gate_aggregate_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
-                g, s, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-                e_out, (T*)e_out_t, m);
+                g, (const T*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
+                e_out, (T*)e_out_t, (T*)gn_t, m);
         });
     }
     CN_LAUNCH_CHECK();
@@ -605,38 +634,40 @@ int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t n
     return 0;
 }
 
-int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
+int cartnet_edge_gate_bwd_reduce(const void* gn_t, const void* s_t, const float* dist, const int32_t* dst32,
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
-                                 const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
-                                 float eps, float radius, int32_t use_envelope, void* ds_t, float* dghat, int32_t prec,
-                                 float* sums, double* partial, cartnet_stream_t stream) {
-    CN_CHECK_ARG(g && s && dist && dst32 && dm && bn_mean && bn_var && ds_t && dghat && sums && partial &&
-                     num_edges > 0, "edge_gate_bwd_reduce: bad arguments");
+                                 const float* bn_weight, const float* bn_bias, float radius, int32_t use_envelope,
+                                 void* ds_t, void* dghat_t, int32_t prec, float* sums, double* partial,
+                                 cartnet_stream_t stream) {
+    CN_CHECK_ARG(gn_t && s_t && dist && dst32 && dm && ds_t && dghat_t && sums && partial && num_edges > 0,
+                 "edge_gate_bwd_reduce: bad arguments");
     CN_CHECK_ARG(colreduce_shape_ok(D), "edge_gate_bwd_reduce: unsupported D=%d", D);
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == CARTNET_PREC_FP32) {
-        EdgeBwdF<float, false> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-                                 (float*)ds_t, dghat};
+        EdgeBwdF<float, false> f{(const float*)gn_t, (const float*)s_t, dist, dst32, de_out, dm, D, bn_weight, bn_bias, radius,
+                                 use_envelope, (float*)ds_t, (float*)dghat_t};
         return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
     }
     CN_DISPATCH_PREC(prec, {
-        EdgeBwdF<T, true> f{g, s, dist, dst32, de_out, dm, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-                            (T*)ds_t, dghat};
+        EdgeBwdF<T, true> f{(const T*)gn_t, (const T*)s_t, dist, dst32, de_out, dm, D, bn_weight, bn_bias, radius, use_envelope,
+                            (T*)ds_t, (T*)dghat_t};
         return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
     });
     return 0;
 }
 
-int cartnet_edge_gate_bwd_apply(const float* g, const float* dghat, int64_t num_edges, int32_t D, const float* bn_mean,
-                                const float* bn_var, const float* bn_weight, float eps, const float* sums,
-                                int32_t training, void* dg_t, int32_t prec, cartnet_stream_t stream) {
-    CN_CHECK_ARG(g && dghat && bn_mean && bn_var && dg_t && D % 4 == 0, "edge_gate_bwd_apply: bad arguments");
+int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t num_edges, int32_t D, const float* bn_var,
+                                const float* bn_weight, float eps, const float* sums, int32_t training, void* dg_t,
+                                int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(gn_t && dghat_t && bn_var && dg_t && row_shape_ok(D), "edge_gate_bwd_apply: bad arguments");
     CN_CHECK_ARG(!training || sums, "edge_gate_bwd_apply: sums required in training mode");
     if (num_edges <= 0) return 0;
-    const int64_t total4 = num_edges * D / 4;
+    const int lanes = 256 / (D / 4);
+    int64_t blocks = ceil_div64(num_edges, (int64_t)lanes * 8);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     CN_DISPATCH_PREC(prec, {
-        edge_bwd_apply_kernel<T><<<(unsigned)ceil_div64(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-            g, dghat, total4, D, num_edges, bn_mean, bn_var, bn_weight, eps, sums, training, (T*)dg_t);
+        edge_bwd_apply_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const T*)gn_t, (const T*)dghat_t, num_edges, D, bn_var, bn_weight, eps, sums, training, (T*)dg_t);
     });
     CN_LAUNCH_CHECK();
     return 0;

@@ -8,7 +8,7 @@
 namespace cartnet {
 
 int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st);   // bf16 or tf32 by d.prec                                  // gemm_tc.cu
-int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C,
+int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, const TnDst& C,
                int64_t ldc, float* ws, int64_t ws_bytes, cudaStream_t st);                 // gemm_tc.cu
 int64_t gemm_tc_tn_workspace(int prec, int M, int N, int64_t K);
 
@@ -124,9 +124,9 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
     }
 }
 
-// C[m,n] = sum_z partial[z][m][n]  (fixed order -> deterministic)
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C,
-                                     int64_t ldc) {
+// C_b[m', n] = sum_z partial[z][m][n]  (fixed order -> deterministic); rows are split into equal blocks b = m / rows_per_blk
+// with their own destination base (the wgrad of a row-packed weight goes straight into the reference's layout)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, TnDst dst, int64_t ldc) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // over M*N/4
     const int64_t total4 = (int64_t)M * N / 4;
     if (i >= total4) return;
@@ -137,7 +137,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
         float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)z * M * N + lin);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n) = s;
+    const int blk = m / dst.rows_per_blk;
+    *reinterpret_cast<float4*>(dst.c[blk] + (int64_t)(m - blk * dst.rows_per_blk) * ldc + n) = s;
 }
 
 static int simt_tn_splits(int M, int N, int64_t K) {
@@ -148,9 +149,9 @@ static int simt_tn_splits(int M, int N, int64_t K) {
     return (int)(s < 1 ? 1 : s);
 }
 
-int launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int64_t ldc, cudaStream_t st) {
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, const TnDst& dst, int64_t ldc, cudaStream_t st) {
     const int64_t total4 = (int64_t)M * N / 4;
-    splitk_reduce_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc);
+    splitk_reduce_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(partial, splits, M, N, dst, ldc);
     CN_LAUNCH_CHECK();
     return 0;
 }
@@ -188,16 +189,28 @@ int64_t cartnet_gemm_tn_workspace(int32_t prec, int32_t M, int32_t N, int64_t K)
     return (int64_t)simt_tn_splits(M, N, K) * M * N * (int64_t)sizeof(float);
 }
 
-int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A, int64_t lda, const void* B,
-                    int64_t ldb, float* C, int64_t ldc, float* workspace, int64_t workspace_bytes,
-                    cartnet_stream_t stream) {
-    CN_CHECK_ARG(M > 0 && N > 0 && K >= 0 && A && B && C, "gemm_tn: bad arguments");
+int cartnet_gemm_tn_blocks(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                           int64_t ldb, float* const* C_blocks, int32_t num_blocks, int64_t ldc, float* workspace,
+                           int64_t workspace_bytes, cartnet_stream_t stream) {
+    CN_CHECK_ARG(M > 0 && N > 0 && K >= 0 && A && B && C_blocks, "gemm_tn: bad arguments");
+    CN_CHECK_ARG(num_blocks >= 1 && num_blocks <= 4 && M % num_blocks == 0, "gemm_tn: 1..4 equal row blocks (M=%d, blocks=%d)", M, num_blocks);
     CN_CHECK_ARG(M % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, "gemm_tn: M,N,ld* must be multiples of 4");
     CN_CHECK_ARG(workspace && workspace_bytes >= cartnet_gemm_tn_workspace(prec, M, N, K), "gemm_tn: workspace too small");
+    TnDst dst = {};
+    dst.rows_per_blk = M / num_blocks;
+    for (int b = 0; b < num_blocks; ++b) {
+        CN_CHECK_ARG(C_blocks[b], "gemm_tn: null output block %d", b);
+        dst.c[b] = C_blocks[b];
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == CARTNET_PREC_BF16 || prec == CARTNET_PREC_TF32)
-        return gemm_tc_tn(prec, M, N, K, A, lda, B, ldb, C, ldc, workspace, workspace_bytes, st);
+        return gemm_tc_tn(prec, M, N, K, A, lda, B, ldb, dst, ldc, workspace, workspace_bytes, st);
     CN_CHECK_ARG(prec == CARTNET_PREC_FP32, "gemm_tn: unknown prec %d", prec);
+    if (K <= 0) {
+        for (int b = 0; b < num_blocks; ++b)
+            CN_CUDA(cudaMemset2DAsync(dst.c[b], ldc * sizeof(float), 0, (size_t)N * sizeof(float), dst.rows_per_blk, st));
+        return 0;
+    }
     const int splits = simt_tn_splits(M, N, K);
     const int n_tiles = ceil_div(N, BN);
     const int tiles = ceil_div(M, BM) * n_tiles;
@@ -207,7 +220,15 @@ int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A
                                                                              (const float*)B, ldb, none, workspace,
                                                                              n_tiles, k_chunk);
     CN_LAUNCH_CHECK();
-    return launch_splitk_reduce(workspace, splits, M, N, C, ldc, st);
+    return launch_splitk_reduce(workspace, splits, M, N, dst, ldc, st);
+}
+
+int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                    int64_t ldb, float* C, int64_t ldc, float* workspace, int64_t workspace_bytes,
+                    cartnet_stream_t stream) {
+    CN_CHECK_ARG(C, "gemm_tn: null output");
+    float* blocks[1] = {C};
+    return cartnet_gemm_tn_blocks(prec, M, N, K, A, lda, B, ldb, blocks, 1, ldc, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

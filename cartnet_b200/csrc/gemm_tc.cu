@@ -22,7 +22,7 @@
 
 namespace cartnet {
 
-int launch_splitk_reduce(const float* partial, int splits, int M, int N, float* C, int64_t ldc, cudaStream_t st);
+int launch_splitk_reduce(const float* partial, int splits, int M, int N, const TnDst& dst, int64_t ldc, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -603,7 +603,8 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     }
     CN_NT_CASE(EB_OUTT)                                                   // node projections P
     CN_NT_CASE(EB_BIAS | EB_GATHER | EB_ZOUT | EB_SILU | EB_OUTT)         // first Linear of both MLPs (per edge)
-    CN_NT_CASE(EB_BIAS | EB_OUTF)                                         // second Linears -> g, s
+    CN_NT_CASE(EB_BIAS | EB_OUTF)                                         // second Linear of MLP_gate -> g (fp32: BatchNorm input)
+    CN_NT_CASE(EB_BIAS | EB_OUTT)                                         // second Linear of MLP_aggr -> s (T)
     CN_NT_CASE(EB_DSILU | EB_OUTT)                                        // dgrad through the second Linears
     CN_NT_CASE(EB_RESID | EB_OUTF)                                        // dgrad to e / x with the residual
     CN_NT_CASE(EB_OUTF)                                                   // dgrad to e when no gradient enters e_out (last layer)
@@ -653,7 +654,7 @@ int64_t gemm_tc_tn_workspace(int prec, int M, int N, int64_t K) {
 }
 
 template <typename T>
-static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C,
+static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, const TnDst& C,
                   int64_t ldc, float* ws, cudaStream_t st) {
     using TR = TcTraits<T>;
     const int esize = (int)sizeof(T);
@@ -675,10 +676,11 @@ static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda,
     return launch_splitk_reduce(ws, p.splits, M, N, C, ldc, st);
 }
 
-int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, float* C,
+int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, const TnDst& C,
                int64_t ldc, float* ws, int64_t ws_bytes, cudaStream_t st) {
     if (K <= 0) {
-        CN_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+        for (int b = 0; b < M / C.rows_per_blk; ++b)
+            CN_CUDA(cudaMemset2DAsync(C.c[b], ldc * sizeof(float), 0, (size_t)N * sizeof(float), C.rows_per_blk, st));
         return 0;
     }
     if (prec == CARTNET_PREC_BF16) return run_tn<__nv_bfloat16>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);

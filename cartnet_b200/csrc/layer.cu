@@ -82,8 +82,10 @@ int64_t cartnet_layer_splitk_bytes(int32_t prec, int32_t D, int32_t num_nodes, i
     int64_t a = cartnet_gemm_tn_workspace(prec, D, D, num_edges);
     int64_t b = cartnet_gemm_tn_workspace(prec, D, D, num_nodes);
     int64_t c = cartnet_gemm_tn_workspace(prec, 2 * D, D, num_edges);
+    int64_t d = cartnet_gemm_tn_workspace(prec, 4 * D, D, num_nodes);
     int64_t m = a > b ? a : b;
-    return (m > c ? m : c) + 256;
+    if (c > m) m = c;
+    return (m > d ? m : d) + 256;
 }
 
 int cartnet_layer_pack_weights(const cartnet_layer_t* L, cartnet_stream_t stream) {
@@ -127,7 +129,7 @@ int cartnet_layer_fwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         dg.bias = L->bg2; dg.out_f32 = L->g; dg.ldo = D;
         CN_TRY(cartnet_gemm(&dg, st));
         cartnet_gemm_t ds = gemm_desc(prec, (int)E, D, D, toff((const void*)L->H, prec, D), 2 * D, L->A2_t, D);
-        ds.bias = L->ba2; ds.out_f32 = L->s; ds.ldo = D;
+        ds.bias = L->ba2; ds.out_t = L->s_t; ds.ldt = D;
         CN_TRY(cartnet_gemm(&ds, st));
     }
     // edge BatchNorm statistics (global barrier over E rows)                         (cartnet.py:238)
@@ -136,8 +138,8 @@ int cartnet_layer_fwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         CN_TRY(cartnet_colstats(L->g, E, D, D, L->mean1, L->var1, L->bn1_rm, L->bn1_rv, L->momentum1, L->partial, st));
         mean1 = L->mean1; var1 = L->var1;
     }
-    CN_TRY(cartnet_edge_gate_aggregate(L->g, L->s, L->e, L->dist, L->row_ptr, N, E, D, mean1, var1, L->bn1_w, L->bn1_b, L->eps,
-                                       L->radius, L->use_envelope, L->e_out, L->e_out_t, prec, L->m, st));
+    CN_TRY(cartnet_edge_gate_aggregate(L->g, L->s_t, L->e, L->dist, L->row_ptr, N, E, D, mean1, var1, L->bn1_w, L->bn1_b, L->eps,
+                                       L->radius, L->use_envelope, L->e_out, L->e_out_t, L->gn_t, prec, L->m, st));
     if (L->training) {
         CN_TRY(cartnet_colstats(L->m, N, D, D, L->mean2, L->var2, L->bn2_rm, L->bn2_rv, L->momentum2, L->partial, st));
         mean2 = L->mean2; var2 = L->var2;
@@ -149,15 +151,15 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     CN_CHECK_ARG(L && L->dx_out, "layer_bwd: null gradient input");      // de_out may be null (= zero)
     const int D = L->D, N = L->num_nodes, prec = L->prec;
     const int64_t E = L->num_edges;
-    const float *mean1 = L->training ? L->mean1 : L->bn1_rm, *var1 = L->training ? L->var1 : L->bn1_rv;
+    const float* var1 = L->training ? L->var1 : L->bn1_rv;
     const float *mean2 = L->training ? L->mean2 : L->bn2_rm, *var2 = L->training ? L->var2 : L->bn2_rv;
     // node side: x' = silu(BN2(m)) + x
     CN_TRY(cartnet_node_update_bwd_reduce(L->dx_out, L->m, N, D, mean2, var2, L->bn2_w, L->bn2_b, L->eps, L->sums2, L->partial, st));
     CN_TRY(cartnet_node_update_bwd_apply(L->dx_out, L->m, N, D, mean2, var2, L->bn2_w, L->bn2_b, L->eps, L->sums2, L->training, L->dm, st));
     // edge side: sig = env * sigmoid(BN1(g)); e' = e + sig; m = segsum(sig * s)
-    CN_TRY(cartnet_edge_gate_bwd_reduce(L->g, L->s, L->dist, L->dst32, L->de_out, L->dm, E, D, mean1, var1, L->bn1_w, L->bn1_b, L->eps,
-                                        L->radius, L->use_envelope, L->ds_t, L->dghat, prec, L->sums1, L->partial, st));
-    CN_TRY(cartnet_edge_gate_bwd_apply(L->g, L->dghat, E, D, mean1, var1, L->bn1_w, L->eps, L->sums1, L->training, L->dg_t, prec, st));
+    CN_TRY(cartnet_edge_gate_bwd_reduce(L->gn_t, L->s_t, L->dist, L->dst32, L->de_out, L->dm, E, D, L->bn1_w, L->bn1_b, L->radius,
+                                        L->use_envelope, L->ds_t, L->dghat_t, prec, L->sums1, L->partial, st));
+    CN_TRY(cartnet_edge_gate_bwd_apply(L->gn_t, L->dghat_t, E, D, var1, L->bn1_w, L->eps, L->sums1, L->training, L->dg_t, prec, st));
     bias_grad_kernel<<<ceil_div(D, 128), 128, 0, (cudaStream_t)st>>>(L->sums1, L->sums2, L->bn1_w, var1, L->eps, L->training, D, L->dba2,
                                                                       L->dbg2, L->dbn1_w, L->dbn1_b, L->dbn2_w, L->dbn2_b);
     CN_LAUNCH_CHECK();
@@ -180,8 +182,10 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         CN_TRY(cartnet_gemm(&d, st));
     }
     // d(W_e) = dZ^T e, written block-wise into the reference layout dG1[:, 2D:3D], dA1[:, 2D:3D]
-    CN_TRY(cartnet_gemm_tn(prec, D, D, E, L->dZ, 2 * D, L->e_t, D, L->dG1 + 2 * D, 3 * D, L->splitk, L->splitk_bytes, st));
-    CN_TRY(cartnet_gemm_tn(prec, D, D, E, toff((const void*)L->dZ, prec, D), 2 * D, L->e_t, D, L->dA1 + 2 * D, 3 * D, L->splitk, L->splitk_bytes, st));
+    {
+        float* blocks[2] = {L->dG1 + 2 * D, L->dA1 + 2 * D};
+        CN_TRY(cartnet_gemm_tn_blocks(prec, 2 * D, D, E, L->dZ, 2 * D, L->e_t, D, blocks, 2, 3 * D, L->splitk, L->splitk_bytes, st));
+    }
     // first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
     CN_TRY(cartnet_segment_sum(L->dZ, 2 * D, L->row_ptr, nullptr, N, 2 * D, L->dP, 4 * D, 1, prec, st));
     CN_TRY(cartnet_segment_sum(L->dZ, 2 * D, L->col_ptr, L->perm_src, N, 2 * D, toff(L->dP, prec, 2 * D), 4 * D, 1, prec, st));
@@ -194,10 +198,9 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         CN_TRY(cartnet_gemm(&d, st));
     }
     // d(W_i), d(W_j) = dP^T x, four [D,D] blocks: G1_i, A1_i, G1_j, A1_j
-    for (int blk = 0; blk < 4; ++blk) {
-        float* dst = ((blk & 1) ? L->dA1 : L->dG1) + (blk >> 1) * D;
-        CN_TRY(cartnet_gemm_tn(prec, D, D, N, toff((const void*)L->dP, prec, (int64_t)blk * D), 4 * D, L->x_t, D, dst, 3 * D, L->splitk,
-                               L->splitk_bytes, st));
+    {
+        float* blocks[4] = {L->dG1, L->dA1, L->dG1 + D, L->dA1 + D};
+        CN_TRY(cartnet_gemm_tn_blocks(prec, 4 * D, D, N, L->dP, 4 * D, L->x_t, D, blocks, 4, 3 * D, L->splitk, L->splitk_bytes, st));
     }
     return 0;
 }

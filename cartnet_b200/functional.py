@@ -112,17 +112,17 @@ class _LayerFn(torch.autograd.Function):
         ops.gemm(prec, e_t, W1e_t, bias=b1.detach(), gather0=P[:, :2 * D], gidx0=plan.dst32,
                  gather1=P[:, 2 * D:], gidx1=plan.src32, z_out=Z, act=ACT_SILU, out_t=H)
         # second Linears                                                              (cartnet.py:190,195)
-        g = torch.empty(E, D, dtype=torch.float32, device=dev)
-        s = torch.empty(E, D, dtype=torch.float32, device=dev)
+        g = torch.empty(E, D, dtype=torch.float32, device=dev)      # BatchNorm input: fp32, scratch after this pass
+        s = torch.empty(E, D, dtype=T, device=dev)
         ops.gemm(prec, H[:, :D], G2_t, bias=bg2.detach(), out_f32=g)
-        ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_f32=s)
+        ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_t=s)
         # edge BatchNorm statistics (global barrier over E rows)                      (cartnet.py:238)
         if training:
             mean1, var1 = ops.colstats(g, cfg["rm1"], cfg["rv1"], cfg["momentum1"])
         else:
             mean1, var1 = cfg["rm1"], cfg["rv1"]
-        e_out, e_out_t, m = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
-                                                    b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True)
+        e_out, e_out_t, m, gn = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
+                                                        b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True)
         if training:
             mean2, var2 = ops.colstats(m, cfg["rm2"], cfg["rv2"], cfg["momentum2"])
         else:
@@ -130,20 +130,20 @@ class _LayerFn(torch.autograd.Function):
         x_out, x_out_t = ops.node_update(m, x, mean2, var2, w2.detach(), b2n.detach(), prec, True)   # cartnet.py:269,223
         cfg["holder"]["x_t"], cfg["holder"]["e_t"] = x_out_t, e_out_t
 
-        ctx.save_for_backward(x_t, e_t, Z, H, g, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
+        ctx.save_for_backward(x_t, e_t, Z, H, gn, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
         ctx.cfg = dict(prec=prec, plan=plan, dist=dist, training=training, radius=cfg["radius"],
                        use_envelope=cfg["use_envelope"])
         return x_out, e_out
 
     @staticmethod
     def backward(ctx, dx_out, de_out):
-        (x_t, e_t, Z, H, g, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n) = ctx.saved_tensors
+        (x_t, e_t, Z, H, gn, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n) = ctx.saved_tensors
         c = ctx.cfg
         prec, plan, training = c["prec"], c["plan"], c["training"]
         T = t_dtype(prec)
-        dev = g.device
+        dev = gn.device
         N, D = int(m.shape[0]), int(m.shape[1])
-        E = int(g.shape[0])
+        E = int(gn.shape[0])
         if dx_out is None:
             dx_out = torch.zeros(N, D, dtype=torch.float32, device=dev)
         if de_out is None:
@@ -154,7 +154,7 @@ class _LayerFn(torch.autograd.Function):
         # node side: x' = silu(BN2(m)) + x
         dm, sums2 = ops.node_update_bwd(dx_out, m, mean2, var2, w2, b2n, training)
         # edge side: sig = env * sigmoid(BN1(g)); e' = e + sig; m = segsum(sig * s)
-        ds_t, dg_t, sums1 = ops.edge_gate_bwd(g, s, c["dist"], plan.dst32, de_out, dm, mean1, var1, w1, b1n,
+        ds_t, dg_t, sums1 = ops.edge_gate_bwd(gn, s, c["dist"], plan.dst32, de_out, dm, var1, w1, b1n,
                                               c["radius"], c["use_envelope"], training, prec)
         # second Linears: dgrad (+ SiLU') and wgrad
         dZ = torch.empty(E, 2 * D, dtype=T, device=dev)
@@ -237,11 +237,13 @@ class _NativeLayerFn(torch.autograd.Function):
             e_t = ops.cast(e, prec)
         shadow = needs_shadow(prec)
         DD = D * D
-        tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D, dtype=T, device=dev)
-        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H) = _carve(tbuf, [
-            (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D)])
-        fbuf = torch.empty(2 * E * D + N * D + 6 * D, dtype=torch.float32, device=dev)
-        g, s, m, mean1, var1, mean2, var2, b1 = _carve(fbuf, [(E, D), (E, D), (N, D), (D,), (D,), (D,), (D,), (2 * D,)])
+        tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D + 2 * E * D, dtype=T, device=dev)
+        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H, s_t, gn_t) = _carve(tbuf, [
+            (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D),
+            (E, D), (E, D)])
+        g = torch.empty(E, D, dtype=torch.float32, device=dev)       # BatchNorm input; not kept for backward
+        fbuf = torch.empty(N * D + 6 * D, dtype=torch.float32, device=dev)
+        m, mean1, var1, mean2, var2, b1 = _carve(fbuf, [(N, D), (D,), (D,), (D,), (D,), (2 * D,)])
         x_out = torch.empty(N, D, dtype=torch.float32, device=dev)
         e_out = torch.empty(E, D, dtype=torch.float32, device=dev)
         x_out_t = torch.empty(N, D, dtype=T, device=dev) if shadow else None
@@ -259,7 +261,7 @@ class _NativeLayerFn(torch.autograd.Function):
             setattr(L, k, p(v.detach()))
         L.bn1_rm, L.bn1_rv, L.bn2_rm, L.bn2_rv = p(cfg["rm1"]), p(cfg["rv1"]), p(cfg["rm2"]), p(cfg["rv2"])
         for k, v in dict(W1n_t=W1n_t, W1e_t=W1e_t, G2_t=G2_t, A2_t=A2_t, W1nT_t=W1nT_t, W1eT_t=W1eT_t, G2T_t=G2T_t, A2T_t=A2T_t,
-                         b1=b1, P=P, Z=Z, H=H, g=g, s=s, m=m, mean1=mean1, var1=var1, mean2=mean2, var2=var2, x_out=x_out,
+                         b1=b1, P=P, Z=Z, H=H, g=g, s_t=s_t, gn_t=gn_t, m=m, mean1=mean1, var1=var1, mean2=mean2, var2=var2, x_out=x_out,
                          e_out=e_out, x_out_t=x_out_t, e_out_t=e_out_t, partial=part).items():
             setattr(L, k, p(v))
         st = ops._stream()
@@ -285,10 +287,10 @@ class _NativeLayerFn(torch.autograd.Function):
         dev = ctx.keep[0].device
         dx_out = torch.zeros(N, D, dtype=torch.float32, device=dev) if dx_out is None else dx_out.contiguous()
         de_out = None if de_out is None else de_out.contiguous()      # None: no gradient into e_out (last layer)
-        tbuf = torch.empty(2 * E * D + E * 2 * D + N * 4 * D, dtype=T, device=dev)
-        ds_t, dg_t, dZ, dP = _carve(tbuf, [(E, D), (E, D), (E, 2 * D), (N, 4 * D)])
-        fbuf = torch.empty(N * D + E * D + 5 * D, dtype=torch.float32, device=dev)
-        dm, dghat, sums1, sums2 = _carve(fbuf, [(N, D), (E, D), (3 * D,), (2 * D,)])
+        tbuf = torch.empty(3 * E * D + E * 2 * D + N * 4 * D, dtype=T, device=dev)
+        ds_t, dg_t, dghat_t, dZ, dP = _carve(tbuf, [(E, D), (E, D), (E, D), (E, 2 * D), (N, 4 * D)])
+        fbuf = torch.empty(N * D + 5 * D, dtype=torch.float32, device=dev)
+        dm, sums1, sums2 = _carve(fbuf, [(N, D), (3 * D,), (2 * D,)])
         dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
         de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
         gbuf = torch.empty(8 * D * D + 8 * D, dtype=torch.float32, device=dev)
@@ -298,7 +300,7 @@ class _NativeLayerFn(torch.autograd.Function):
         ws = ops._workspace(dev, nbytes)
         part = ops._partial(dev, int(lib.cartnet_colstats_workspace(2 * D)))
         p = ops._p
-        for k, v in dict(dx_out=dx_out, de_out=de_out, dm=dm, ds_t=ds_t, dg_t=dg_t, dghat=dghat, dZ=dZ, dP=dP, sums1=sums1,
+        for k, v in dict(dx_out=dx_out, de_out=de_out, dm=dm, ds_t=ds_t, dg_t=dg_t, dghat_t=dghat_t, dZ=dZ, dP=dP, sums1=sums1,
                          sums2=sums2, dx_in=dx_in, de_in=de_in, dG1=dG1, dA1=dA1, dbg1=dbg1, dba1=dba1, dG2=dG2, dA2=dA2,
                          dbg2=dbg2, dba2=dba2, dbn1_w=dw1, dbn1_b=db1n, dbn2_w=dw2, dbn2_b=db2n, partial=part, splitk=ws).items():
             setattr(L, k, p(v))

@@ -250,20 +250,31 @@ def gemm(prec: int, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, 
     _lib.check(lib.cartnet_gemm(C.byref(d), _stream()), "gemm")
 
 
-def gemm_tn(prec: int, A, B) -> torch.Tensor:
-    """C[M,N] fp32 = A[K,M]^T @ B[K,N] (deterministic split-K)."""
+def gemm_tn(prec: int, A, B, out_blocks=None) -> torch.Tensor:
+    """C[M,N] fp32 = A[K,M]^T @ B[K,N] (deterministic split-K). With out_blocks = [v_0 .. v_{b-1}] (b <= 4 fp32 views
+    of shape [M/b, N] sharing one row pitch) row block i of C is written into v_i instead of a fresh tensor."""
     lib = _lib.load()
     T = t_dtype(prec)
     _req(A, T, "A"); _req(B, T, "B")
     K, M, N = int(A.shape[0]), int(A.shape[1]), int(B.shape[1])
     if int(B.shape[0]) != K:
         raise ValueError("gemm_tn: K mismatch")
-    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     nbytes = int(lib.cartnet_gemm_tn_workspace(prec, M, N, K))
     ws = _workspace(A.device, nbytes)
-    _lib.check(lib.cartnet_gemm_tn(prec, M, N, K, _p(A), _ld2(A), _p(B), _ld2(B), _p(out), N, _p(ws),
-                                   ws.numel() * 4, _stream()), "gemm_tn")
-    return out
+    if out_blocks is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+        _lib.check(lib.cartnet_gemm_tn(prec, M, N, K, _p(A), _ld2(A), _p(B), _ld2(B), _p(out), N, _p(ws),
+                                       ws.numel() * 4, _stream()), "gemm_tn")
+        return out
+    nb = len(out_blocks)
+    for v in out_blocks:
+        _req(v, torch.float32, "out_blocks[i]")
+        if tuple(v.shape) != (M // nb, N) or _ld2(v) != _ld2(out_blocks[0]):
+            raise ValueError("gemm_tn: out_blocks must be %d views of shape [%d,%d] with one row pitch" % (nb, M // nb, N))
+    ptrs = (C.c_void_p * nb)(*[v.data_ptr() for v in out_blocks])
+    _lib.check(lib.cartnet_gemm_tn_blocks(prec, M, N, K, _p(A), _ld2(A), _p(B), _ld2(B), ptrs, nb, _ld2(out_blocks[0]),
+                                          _p(ws), ws.numel() * 4, _stream()), "gemm_tn_blocks")
+    return out_blocks
 
 
 # ----------------------------------------------------------------------------- reductions
@@ -293,21 +304,25 @@ def colsum(x, prec: int) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- layer passes
 def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes: int, bn_mean, bn_var, bn_w, bn_b, radius: float,
-                        use_envelope: bool, prec: int, want_shadow: bool):
+                        use_envelope: bool, prec: int, want_shadow: bool, want_gn: bool = True):
+    """g fp32 (BatchNorm input), s T. Returns e_out (fp32), its T shadow, m, and gn_t = (g-mean)*rstd in T (what the
+    backward pass reads instead of g)."""
     lib = _lib.load()
-    for nm, t in (("g", g), ("s", s), ("e", e)):
-        _req(t, torch.float32, nm)
+    T = t_dtype(prec)
+    for nm, t, dt in (("g", g, torch.float32), ("s", s, T), ("e", e, torch.float32)):
+        _req(t, dt, nm)
         if not t.is_contiguous():
             raise ValueError("%s must be contiguous" % nm)
     E, D = int(e.shape[0]), int(e.shape[1])
     e_out = torch.empty_like(e)
-    e_out_t = torch.empty(E, D, dtype=t_dtype(prec), device=e.device) if (want_shadow and needs_shadow(prec)) else None
+    e_out_t = torch.empty(E, D, dtype=T, device=e.device) if (want_shadow and needs_shadow(prec)) else None
+    gn_t = torch.empty(E, D, dtype=T, device=e.device) if want_gn else None
     m = torch.empty(num_nodes, D, dtype=torch.float32, device=e.device)
     _lib.check(lib.cartnet_edge_gate_aggregate(
         _p(g), _p(s), _p(e), _p(dist), _p(row_ptr), num_nodes, E, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b),
-        EPS_BN, float(radius), int(bool(use_envelope)), _p(e_out), _p(e_out_t), prec, _p(m), _stream()),
+        EPS_BN, float(radius), int(bool(use_envelope)), _p(e_out), _p(e_out_t), _p(gn_t), prec, _p(m), _stream()),
         "edge_gate_aggregate")
-    return e_out, (e_out_t if e_out_t is not None else (e_out if not needs_shadow(prec) else None)), m
+    return e_out, (e_out_t if e_out_t is not None else (e_out if not needs_shadow(prec) else None)), m, gn_t
 
 
 def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec: int, want_shadow: bool):
@@ -338,24 +353,28 @@ def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training: bool):
     return dm, sums
 
 
-def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, radius: float, use_envelope: bool,
+def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius: float, use_envelope: bool,
                   training: bool, prec: int):
-    """Returns ds_t, dg_t (T, [E,D]) and sums [3D]: sum dghat (= d bias of the edge BatchNorm) | sum dghat*ghat_norm
+    """gn_t, s_t: the T tensors saved by edge_gate_aggregate / the MLP_aggr GEMM. de_out may be None (= zero).
+    Returns ds_t, dg_t (T, [E,D]) and sums [3D]: sum dghat (= d bias of the edge BatchNorm) | sum dghat*gn
     (= d weight) | sum ds (= d bias of MLP_aggr[2])."""
     lib = _lib.load()
-    de_out = _req(de_out.contiguous(), torch.float32, "de_out")
-    E, D = int(g.shape[0]), int(g.shape[1])
     T = t_dtype(prec)
-    ds_t = torch.empty(E, D, dtype=T, device=g.device)
-    dg_t = torch.empty(E, D, dtype=T, device=g.device)
-    dghat = torch.empty(E, D, dtype=torch.float32, device=g.device)
-    sums = torch.empty(3 * D, dtype=torch.float32, device=g.device)
-    part = _partial(g.device, int(lib.cartnet_colstats_workspace(D)))
+    _req(gn_t, T, "gn_t"); _req(s_t, T, "s_t")
+    if de_out is not None:
+        de_out = _req(de_out.contiguous(), torch.float32, "de_out")
+    E, D = int(gn_t.shape[0]), int(gn_t.shape[1])
+    dev = gn_t.device
+    ds_t = torch.empty(E, D, dtype=T, device=dev)
+    dg_t = torch.empty(E, D, dtype=T, device=dev)
+    dghat_t = torch.empty(E, D, dtype=T, device=dev)
+    sums = torch.empty(3 * D, dtype=torch.float32, device=dev)
+    part = _partial(dev, int(lib.cartnet_colstats_workspace(D)))
     st = _stream()
     _lib.check(lib.cartnet_edge_gate_bwd_reduce(
-        _p(g), _p(s), _p(dist), _p(dst32), _p(de_out), _p(dm), E, D, _p(bn_mean), _p(bn_var), _p(bn_w), _p(bn_b), EPS_BN,
-        float(radius), int(bool(use_envelope)), _p(ds_t), _p(dghat), prec, _p(sums), _p(part), st), "edge_gate_bwd_reduce")
-    _lib.check(lib.cartnet_edge_gate_bwd_apply(_p(g), _p(dghat), E, D, _p(bn_mean), _p(bn_var), _p(bn_w), EPS_BN,
+        _p(gn_t), _p(s_t), _p(dist), _p(dst32), _p(de_out), _p(dm), E, D, _p(bn_w), _p(bn_b),
+        float(radius), int(bool(use_envelope)), _p(ds_t), _p(dghat_t), prec, _p(sums), _p(part), st), "edge_gate_bwd_reduce")
+    _lib.check(lib.cartnet_edge_gate_bwd_apply(_p(gn_t), _p(dghat_t), E, D, _p(bn_var), _p(bn_w), EPS_BN,
                                                _p(sums), int(bool(training)), _p(dg_t), prec, st), "edge_gate_bwd_apply")
     return ds_t, dg_t, sums
 

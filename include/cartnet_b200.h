@@ -152,6 +152,13 @@ int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A
                     const void* B, int64_t ldb, float* C, int64_t ldc, float* workspace,
                     int64_t workspace_bytes, cartnet_stream_t stream);
 
+/* Same, with the M output rows split into num_blocks (1..4) equal blocks that are written to separate bases
+ * C_blocks[b] (host array of device pointers, each [M/num_blocks, N] with pitch ldc): the gradient of a row-packed
+ * weight ([G1_e;A1_e], [G1_i;A1_i;G1_j;A1_j]) lands directly in the reference's [D,3D] parameter layout. */
+int cartnet_gemm_tn_blocks(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A, int64_t lda,
+                           const void* B, int64_t ldb, float* const* C_blocks, int32_t num_blocks, int64_t ldc,
+                           float* workspace, int64_t workspace_bytes, cartnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Column statistics / BatchNorm pieces -- replace nn.BatchNorm1d over E rows (cartnet.py:198,238)
  * and over N rows (cartnet.py:199,269). Sums are accumulated in fp64 in a fixed order.
@@ -178,12 +185,14 @@ int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, in
 /* Forward edge pass:  ghat = BN(g); sig = env(dist) * sigmoid(ghat); e_out = e + sig;
  * m[i] = sum_{edges -> i, CSR order} sig * s   (deterministic, no atomics).
  * env(d) = 0.5 (cos(pi d / radius) + 1) (d < radius) when use_envelope else 1.
- * e_out_t (T shadow for the next layer's GEMM operand) may be null. */
-int cartnet_edge_gate_aggregate(const float* g, const float* s, const float* e, const float* dist,
+ * g is fp32 (BatchNorm input), s_t is T. e_out_t (T shadow for the next layer's GEMM operand) may be null.
+ * gn_t (T, may be null) receives the normalised pre-activation (g - mean) * rstd: with s_t it is all the
+ * backward pass needs, so g itself is scratch. */
+int cartnet_edge_gate_aggregate(const float* g, const void* s_t, const float* e, const float* dist,
                                 const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
                                 const float* bn_mean, const float* bn_var, const float* bn_weight,
                                 const float* bn_bias, float eps, float radius, int32_t use_envelope,
-                                float* e_out, void* e_out_t, int32_t prec, float* m,
+                                float* e_out, void* e_out_t, void* gn_t, int32_t prec, float* m,
                                 cartnet_stream_t stream);
 
 /* Forward node pass: x_out = silu(BN2(m)) + x ; x_out_t optional T shadow. */
@@ -205,21 +214,21 @@ int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t n
                                   const float* bn_bias, float eps, const float* sums, int32_t training,
                                   float* dm, cartnet_stream_t stream);
 
-/* Backward edge pass, step 1 (per edge, channel):  dmd = dm[dst];  ds = sig * dmd  -> ds_t (T);
- * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat (fp32);
- * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * ghat_norm, sums[2D:3D] = sum_e ds (sums has 3D entries).
+/* Backward edge pass, step 1 (per edge, channel), from the saved gn_t / s_t (both T):
+ * ghat = gn * weight + bias; sig = env * sigmoid(ghat); dmd = dm[dst];  ds = sig * dmd  -> ds_t (T);
+ * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat_t (T);
+ * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * gn, sums[2D:3D] = sum_e ds (sums has 3D entries; the sums
+ * are taken before the rounding to T).
  * de_out may be null (no gradient flows into e_out, e.g. the last layer: the heads read only x). */
-int cartnet_edge_gate_bwd_reduce(const float* g, const float* s, const float* dist, const int32_t* dst32,
+int cartnet_edge_gate_bwd_reduce(const void* gn_t, const void* s_t, const float* dist, const int32_t* dst32,
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
-                                 const float* bn_mean, const float* bn_var, const float* bn_weight,
-                                 const float* bn_bias, float eps, float radius, int32_t use_envelope,
-                                 void* ds_t, float* dghat, int32_t prec, float* sums, double* partial,
-                                 cartnet_stream_t stream);
-/* step 2: dg = weight*rstd*(dghat - [train](sum/E + ghat_norm*sum2/E)) -> dg_t (T). */
-int cartnet_edge_gate_bwd_apply(const float* g, const float* dghat, int64_t num_edges, int32_t D,
-                                const float* bn_mean, const float* bn_var, const float* bn_weight,
-                                float eps, const float* sums, int32_t training, void* dg_t, int32_t prec,
-                                cartnet_stream_t stream);
+                                 const float* bn_weight, const float* bn_bias, float radius,
+                                 int32_t use_envelope, void* ds_t, void* dghat_t, int32_t prec, float* sums,
+                                 double* partial, cartnet_stream_t stream);
+/* step 2: dg = weight*rstd*(dghat - [train](sum/E + gn*sum2/E)) -> dg_t (T). */
+int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t num_edges, int32_t D,
+                                const float* bn_var, const float* bn_weight, float eps, const float* sums,
+                                int32_t training, void* dg_t, int32_t prec, cartnet_stream_t stream);
 
 /* out[n, 0:C] = sum over CSR row n of x[perm[k], 0:C] (perm may be null = identity). x is T,
  * out is T (out_is_t=1) or fp32. Used for d(P_i) (dst CSR) and d(P_j) (src CSR) -- the transpose of the
@@ -264,7 +273,8 @@ typedef struct cartnet_layer {
     float* b1;
     /* forward: saved activations and outputs */
     void *P, *Z, *H;                                 /* T: [N,4D], [E,2D], [E,2D] */
-    float *g, *s, *m;                                /* [E,D], [E,D], [N,D] */
+    float *g, *m;                                    /* [E,D] (scratch after the forward pass), [N,D] */
+    void *s_t, *gn_t;                                /* T [E,D]: MLP_aggr output, normalised gate pre-activation (saved) */
     float *mean1, *var1, *mean2, *var2;              /* [D] statistics used (batch or running) */
     float *x_out, *e_out;                            /* [N,D], [E,D] */
     void *x_out_t, *e_out_t;                         /* T copies for the next layer (null when T = float) */
@@ -272,7 +282,7 @@ typedef struct cartnet_layer {
     const float *dx_out, *de_out;                    /* de_out may be null: treated as zero without being read */
     float* dm;                                       /* [N,D] */
     void *ds_t, *dg_t;                               /* T [E,D] */
-    float* dghat;                                    /* [E,D] */
+    void* dghat_t;                                   /* T [E,D] */
     void *dZ, *dP;                                   /* T [E,2D], [N,4D] */
     float *sums1, *sums2;                            /* [3D], [2D] */
     float *dx_in, *de_in;                            /* [N,D], [E,D] */

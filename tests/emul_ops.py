@@ -132,15 +132,15 @@ def colsum(x, prec):
 
 
 def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes, bn_mean, bn_var, bn_w, bn_b, radius, use_envelope, prec,
-                        want_shadow):
-    ghat, _, _ = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+                        want_shadow, want_gn=True):
+    ghat, gn, _ = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
     sig = _env(_f(dist), radius, use_envelope).unsqueeze(-1) * torch.sigmoid(ghat)
     e_out = (_f(e) + sig).float()
     counts = (row_ptr[1:] - row_ptr[:-1]).long()
     dst = torch.repeat_interleave(torch.arange(num_nodes), counts)
     m = torch.zeros(num_nodes, e.shape[1], dtype=sig.dtype).index_add_(0, dst, sig * _f(s)).float()
     e_t = _shadow(e_out, prec)
-    return e_out, e_t, m
+    return e_out, e_t, m, (_shadow(gn.float(), prec) if want_gn else None)
 
 
 def node_update(m, x, bn_mean, bn_var, bn_w, bn_b, prec, want_shadow):
@@ -159,15 +159,18 @@ def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training):
     return dm.float(), torch.cat([s1, s2]).float()
 
 
-def edge_gate_bwd(g, s, dist, dst32, de_out, dm, bn_mean, bn_var, bn_w, bn_b, radius, use_envelope, training, prec):
-    ghat, gn, rstd = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
-    sg = torch.sigmoid(ghat)
+def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius, use_envelope, training, prec):
+    gn = _f(gn_t)
+    rstd = 1.0 / torch.sqrt(_f(bn_var) + EPS_BN)
+    sg = torch.sigmoid(gn * _f(bn_w) + _f(bn_b))
     env = _env(_f(dist), radius, use_envelope).unsqueeze(-1)
     dmd = _f(dm)[dst32.long()]
     ds = env * sg * dmd
-    dghat = (_f(de_out) + _f(s) * dmd) * env * sg * (1 - sg)
-    s1, s2 = dghat.sum(0), (dghat * gn).sum(0)
-    n = g.shape[0]
+    dsig = _f(s_t) * dmd if de_out is None else _f(de_out) + _f(s_t) * dmd
+    dghat = dsig * env * sg * (1 - sg)
+    s1, s2 = dghat.sum(0), (dghat * gn).sum(0)           # sums are taken before dghat is rounded to T
+    dghat = _f(_shadow(dghat.float(), prec))
+    n = gn.shape[0]
     corr = (s1 / n + gn * s2 / n) if training else 0.0
     dg = _f(bn_w) * rstd * (dghat - corr)
     T = t_dtype(prec)

@@ -75,14 +75,14 @@ def test_config4_supercell_reductions_and_determinism():
     g, sv, e = (torch.randn(E, D, device="cuda", generator=gen) for _ in range(3))
     mean, var = torch.zeros(D, device="cuda"), torch.ones(D, device="cuda")
     w, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
-    e_out, _, m = ops.edge_gate_aggregate(g, sv, e, gr["cart_dist"], plan.row_ptr, N, mean, var, w, b, 5.0, True, ops.PREC_FP32, False)
+    e_out, _, m, _ = ops.edge_gate_aggregate(g, sv, e, gr["cart_dist"], plan.row_ptr, N, mean, var, w, b, 5.0, True, ops.PREC_FP32, False)
     # torch fp32 reference of the same op (index_add_ = what torch_scatter.scatter does, cartnet.py:259)
     ghat = g / torch.sqrt(var + 1e-5)
     env = 0.5 * (torch.cos(gr["cart_dist"] * torch.pi / 5.0) + 1.0) * (gr["cart_dist"] < 5.0)
     sig = env.unsqueeze(-1) * torch.sigmoid(ghat)
     m_ref = torch.zeros(N, D, device="cuda", dtype=torch.float64).index_add_(0, gr["edge_index"][1], (sig * sv).double())
     assert common.rel_err(m, m_ref) < 2e-6 and common.rel_err(e_out, e + sig) < 2e-6
-    e_out2, _, m2 = ops.edge_gate_aggregate(g, sv, e, gr["cart_dist"], plan.row_ptr, N, mean, var, w, b, 5.0, True, ops.PREC_FP32, False)
+    e_out2, _, m2, _ = ops.edge_gate_aggregate(g, sv, e, gr["cart_dist"], plan.row_ptr, N, mean, var, w, b, 5.0, True, ops.PREC_FP32, False)
     assert torch.equal(m, m2)
     # transpose of the src lift: segment sum through the src CSR == index_add over src
     x = torch.randn(E, 512, device="cuda", generator=gen)

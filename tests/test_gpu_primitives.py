@@ -105,6 +105,13 @@ def test_gemm_tn(prec, K, M, N):
     assert common.rel_err(got, ref) < (2e-3 if prec == PREC_TF32 else 5e-6)
     got2 = ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda())
     assert torch.equal(got, got2)                      # deterministic split-K
+    # row blocks scattered into a wider parameter-gradient layout (dG1[:, 2D:3D] / dA1[:, 2D:3D] in cartnet_layer_bwd)
+    nb = M // 256
+    if nb in (2, 4):
+        dest = torch.zeros(nb, 256, 3 * N, device="cuda")
+        ops.gemm_tn(prec, big.cuda()[:, M:], B.cuda(), out_blocks=[dest[i, :, N:2 * N] for i in range(nb)])
+        assert torch.equal(dest[:, :, N:2 * N].reshape(M, N), got)
+        assert float(dest[:, :, :N].abs().max()) == 0.0 and float(dest[:, :, 2 * N:].abs().max()) == 0.0
 
 
 def test_colstats_and_running_update():
@@ -138,17 +145,19 @@ def _graph(N, E, seed):
 def test_edge_gate_aggregate(prec, use_env):
     N, E, D = 301, 17011, 256
     plan = _graph(N, E, 1)
-    g, s, e = rnd(E, D, seed=1), rnd(E, D, seed=2), rnd(E, D, seed=3)
+    g, s, e = rnd(E, D, seed=1), EM.cast(rnd(E, D, seed=2), prec), rnd(E, D, seed=3)
     dist = torch.rand(E, generator=torch.Generator().manual_seed(4)) * 5.5
     mean, var, w, b = _bn_args(D, 5)
     ref, got = both("edge_gate_aggregate", (g, s, e, dist, plan.row_ptr, N, mean, var, w, b, 5.0, use_env, prec, True))
+    tT = 2e-6 if prec == PREC_FP32 else 8e-3
     assert common.rel_err(got[0], ref[0]) < 2e-6
-    assert common.rel_err(got[1].float(), ref[1].float()) < (2e-6 if prec == PREC_FP32 else 8e-3)
+    assert common.rel_err(got[1].float(), ref[1].float()) < tT
     assert common.rel_err(got[2], ref[2]) < 1e-5
+    assert common.rel_err(got[3].float(), ref[3].float()) < tT          # normalised gate pre-activation saved for backward
     assert float(got[2][3].abs().max()) == 0.0             # node without in-edges gets exactly 0
     got2 = ops.edge_gate_aggregate(g.cuda(), s.cuda(), e.cuda(), dist.cuda(), plan.row_ptr.cuda(), N, mean.cuda(), var.cuda(),
-                                   w.cuda(), b.cuda(), 5.0, use_env, prec, True)
-    assert torch.equal(got2[2], got[2])                    # deterministic reduction
+                                   w.cuda(), b.cuda(), 5.0, use_env, prec, True, want_gn=False)
+    assert torch.equal(got2[2], got[2]) and got2[3] is None   # deterministic reduction; gn is optional
 
 
 @pytest.mark.parametrize("training", [True, False])
@@ -164,14 +173,16 @@ def test_node_update_fwd_bwd(training):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("training", [True, False])
-def test_edge_gate_bwd(prec, training):
+@pytest.mark.parametrize("with_de", [True, False])
+def test_edge_gate_bwd(prec, training, with_de):
     N, E, D = 150, 9001, 256
     plan = _graph(N, E, 2)
-    g, s, de = rnd(E, D, seed=1), rnd(E, D, seed=2), rnd(E, D, seed=3)
+    gn, s = EM.cast(rnd(E, D, seed=1), prec), EM.cast(rnd(E, D, seed=2), prec)
+    de = rnd(E, D, seed=3) if with_de else None            # None: no gradient enters e_out (last layer)
     dm = rnd(N, D, seed=4)
     dist = torch.rand(E, generator=torch.Generator().manual_seed(4)) * 5.5
-    mean, var, w, b = _bn_args(D, 5)
-    ref, got = both("edge_gate_bwd", (g, s, dist, plan.dst32, de, dm, mean, var, w, b, 5.0, True, training, prec))
+    _, var, w, b = _bn_args(D, 5)
+    ref, got = both("edge_gate_bwd", (gn, s, dist, plan.dst32, de, dm, var, w, b, 5.0, True, training, prec))
     t = 1e-5 if prec == PREC_FP32 else 8e-3
     assert common.rel_err(got[0].float(), ref[0].float()) < t
     assert common.rel_err(got[1].float(), ref[1].float()) < t
