@@ -40,7 +40,7 @@ class LayerDesc(C.Structure):
               "G1", "A1", "bg1", "ba1", "G2", "A2", "bg2", "ba2", "bn1_w", "bn1_b", "bn2_w", "bn2_b",
               "bn1_rm", "bn1_rv", "bn2_rm", "bn2_rv",
               "W1n_t", "W1e_t", "G2_t", "A2_t", "W1nT_t", "W1eT_t", "G2T_t", "A2T_t", "b1",
-              "P", "Z", "H", "g", "m", "s_t", "gn_t", "mean1", "var1", "mean2", "var2", "x_out", "e_out", "x_out_t", "e_out_t",
+              "P", "Z", "H", "g_t", "center", "bias_c", "hsum", "m", "s_t", "gn_t", "mean1", "var1", "mean2", "var2", "x_out", "e_out", "x_out_t", "e_out_t",
               "dx_out", "de_out", "dm", "ds_t", "dg_t", "dghat_t", "dZ", "dP", "sums1", "sums2", "dx_in", "de_in",
               "dG1", "dA1", "dbg1", "dba1", "dG2", "dA2", "dbg2", "dba2", "dbn1_w", "dbn1_b", "dbn2_w", "dbn2_b",
               "partial", "splitk"]
@@ -65,11 +65,13 @@ SIGNATURES = {
     "cartnet_graph_csr": (i32, [vp, i64, i32, vp, vp, vp, vp]),
     "cartnet_edge_features": (i32, [vp, vp, vp, vp, i32, f32, i32, i64, vp, i32, i32, vp]),
     "cartnet_gemm": (i32, [C.POINTER(GemmDesc), vp]),
+    "cartnet_gemm_colstats": (i32, [C.POINTER(GemmDesc), vp, vp, vp, vp, vp, f32, vp, vp]),
     "cartnet_gemm_tn_workspace": (i64, [i32, i32, i32, i64]),
     "cartnet_gemm_tn": (i32, [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
     "cartnet_gemm_tn_blocks": (i32, [i32, i32, i32, i64, vp, i64, vp, i64, C.POINTER(vp), i32, i64, vp, i64, vp]),
     "cartnet_colstats_workspace": (i64, [i32]),
-    "cartnet_colstats": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, f32, vp, vp]),
+    "cartnet_colstats": (i32, [vp, i32, i32, i64, i32, i64, vp, vp, vp, vp, vp, f32, vp, vp]),
+    "cartnet_gate_center": (i32, [vp, i64, i64, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     "cartnet_colsum": (i32, [vp, i32, i32, i64, i32, i64, vp, vp, vp]),
     "cartnet_edge_gate_aggregate": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, i32, vp, vp]),
     "cartnet_node_update": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, f32, vp, vp, i32, vp]),

@@ -49,6 +49,10 @@ struct TnDst {
     int rows_per_blk;
 };
 
+// mean / biased variance (+ running-statistics update) from fp64 partial sums [nblocks][2][C] (edge_ops.cu)
+int launch_colstats_final(const double* partial, int nblocks, int C, int64_t rows, const float* shift, float* mean, float* var,
+                          float* running_mean, float* running_var, float momentum, cudaStream_t st);
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -112,6 +116,23 @@ __device__ __forceinline__ float4 ldg4<__nv_bfloat16>(const __nv_bfloat16* p) {
     float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
     return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+// raw (unconverted) 4-element loads so that all global reads of a chunk can be issued before any math / store
+template <typename T> struct Raw4;
+template <> struct Raw4<tf32_t> { using type = float4; };
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ld_raw4(const T* p);
+template <> __device__ __forceinline__ float4 ld_raw4<tf32_t>(const tf32_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 ld_raw4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ uint2 ld_raw4<__nv_bfloat16>(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ float4 cvt_raw4(const float4& r) { return r; }
+__device__ __forceinline__ float4 cvt_raw4(const uint2& r) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
 template <typename T>
 __device__ __forceinline__ void store4(T* p, float4 v);
 template <>

@@ -129,7 +129,7 @@ __device__ __forceinline__ double warp_block_sum(const double* __restrict__ part
 __global__ void __launch_bounds__(256)
 colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, int64_t rows, int mode,
                        float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ run_mean,
-                       float* __restrict__ run_var, float momentum, int n_out, int nv) {
+                       float* __restrict__ run_var, float momentum, int n_out, int nv, const float* __restrict__ shift) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per output column
     if (mode == FIN_STATS) {
@@ -145,7 +145,9 @@ colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int C, i
         out1[c] = (float)var;
         if (run_mean) {
             const double unb = rows > 1 ? var * n / (n - 1.0) : var;
-            run_mean[c] = (float)((1.0 - (double)momentum) * (double)run_mean[c] + (double)momentum * mean);
+            // the statistics are those of the stored (possibly centred) tensor; the running mean tracks x + shift
+            const double true_mean = mean + (shift ? (double)shift[c] : 0.0);
+            run_mean[c] = (float)((1.0 - (double)momentum) * (double)run_mean[c] + (double)momentum * true_mean);
             run_var[c] = (float)((1.0 - (double)momentum) * (double)run_var[c] + (double)momentum * unb);
         }
     } else {
@@ -169,7 +171,7 @@ static inline int colreduce_blocks(int64_t rows, int C) {
 
 template <class F>
 static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, float* out0, float* out1, float* rm,
-                         float* rv, float momentum, int n_out, cudaStream_t st) {
+                         float* rv, float momentum, int n_out, cudaStream_t st, const float* shift = nullptr) {
     const int nb = colreduce_blocks(rows, C);
     const int lanes = 256 / (C / 4);
     const size_t smem = (size_t)lanes * F::NV * C * sizeof(double);
@@ -177,21 +179,30 @@ static int run_colreduce(F f, int64_t rows, int C, double* partial, int mode, fl
     CN_LAUNCH_CHECK();
     const int nthreads = mode == FIN_STATS ? C : n_out;
     colreduce_final_kernel<<<ceil_div(nthreads, 8), 256, 0, st>>>(partial, nb, C, rows, mode, out0, out1, rm, rv,
-                                                                 momentum, n_out, F::NV);
+                                                                 momentum, n_out, F::NV, shift);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_colstats_final(const double* partial, int nblocks, int C, int64_t rows, const float* shift, float* mean, float* var,
+                          float* running_mean, float* running_var, float momentum, cudaStream_t st) {
+    colreduce_final_kernel<<<ceil_div(C, 8), 256, 0, st>>>(partial, nblocks, C, rows, FIN_STATS, mean, var, running_mean,
+                                                          running_var, momentum, 0, 2, shift);
     CN_LAUNCH_CHECK();
     return 0;
 }
 
 // ---- functors: init(col) -> State ; load(row, col, In&) ; compute(State, row, col, In, float4 out[NV]) --------
 struct NoState {};
+template <typename TX>
 struct StatsF {
     static constexpr int NV = 2;
     static constexpr bool F32_PARTIAL = false;
     using State = NoState;
     using In = float4;
-    const float* x; int64_t ld;
+    const TX* x; int64_t ld;
     __device__ State init(int) const { return State{}; }
-    __device__ void load(int64_t r, int col, In& in) const { in = __ldg(reinterpret_cast<const float4*>(x + r * ld + col)); }
+    __device__ void load(int64_t r, int col, In& in) const { in = ldg4<TX>(x + r * ld + col); }
     __device__ void compute(const State&, int64_t, int, const In& a, float4* o) const {
         o[0] = a;
         o[1] = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
@@ -298,13 +309,24 @@ template <> __device__ __forceinline__ double cutoff_r<double>(float d, float up
     return d < upper ? 0.5 * (cos((double)arg) + 1.0) : 0.0;
 }
 
-template <typename T, typename R>
-__global__ void __launch_bounds__(256)
-edge_gate_aggregate_kernel(const float* __restrict__ g, const T* __restrict__ s, const float* __restrict__ e,
+// FAST (tensor-core modes): MUFU sigmoid / cosine, like the backward pass; the fp32 parity mode computes in double.
+template <typename R, bool FAST> __device__ __forceinline__ R gate_sigmoid(R v) { return sigmoid_r<R>(v); }
+// forward gate: EX2 + RCP (relative error ~1e-6) rather than tanh.approx (2^-11): sigma is accumulated into the fp32
+// residual stream e over all layers, and the tf32 mode is held to 2e-3 end to end
+template <> __device__ __forceinline__ float gate_sigmoid<float, true>(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+template <typename R, bool FAST> __device__ __forceinline__ R gate_cutoff(float d, float upper) { return cutoff_r<R>(d, upper); }
+template <> __device__ __forceinline__ float gate_cutoff<float, true>(float d, float upper) { return cutoff_sel<true>(d, upper); }
+
+// D/4 threads per destination node walk its CSR row in order (deterministic sum); the loads of U consecutive edges
+// are issued together so that each thread keeps U x 40 bytes in flight.
+template <typename T, typename R, bool FAST>
+__global__ void __launch_bounds__(256, FAST ? 2 : 1)
+edge_gate_aggregate_kernel(const T* __restrict__ g, const T* __restrict__ s, const float* __restrict__ e,
                            const float* __restrict__ dist, const int32_t* __restrict__ row_ptr, int num_nodes, int D,
                            const float* mean, const float* var, const float* w, const float* bias, float eps,
                            float radius, int use_env, float* __restrict__ e_out, T* __restrict__ e_out_t,
                            T* __restrict__ gn_t, float* __restrict__ m) {
+    constexpr int U = 4;
     const int tpr = D >> 2, npb = 256 / tpr;
     const int node = blockIdx.x * npb + threadIdx.x / tpr;
     const int col = (threadIdx.x % tpr) * 4;
@@ -312,27 +334,25 @@ edge_gate_aggregate_kernel(const float* __restrict__ g, const T* __restrict__ s,
     R mu[4], rs[4], sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        mu[j] = (R)mean[col + j];
+        mu[j] = mean ? (R)mean[col + j] : (R)0;              // null mean: g arrives centred on the statistics' mean (eval mode)
         rs[j] = (R)1 / sqrt((R)var[col + j] + (R)eps);
         sc[j] = (w ? (R)w[col + j] : (R)1) * rs[j];
         sh[j] = bias ? (R)bias[col + j] : (R)0;
     }
     R acc[4] = {0, 0, 0, 0};
     const int k0 = row_ptr[node], k1 = row_ptr[node + 1];
-    for (int k = k0; k < k1; ++k) {
+    auto edge = [&](int k, const typename Raw4<T>::type& gr, const typename Raw4<T>::type& sr, const float4& e4, float dk) {
         const int64_t o = (int64_t)k * D + col;
-        const float4 g4 = *reinterpret_cast<const float4*>(g + o);
-        const float4 s4 = load4<T>(s + o);
-        const float4 e4 = *reinterpret_cast<const float4*>(e + o);
+        const float4 g4 = cvt_raw4(gr), s4 = cvt_raw4(sr);
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
-        const R env = use_env ? cutoff_r<R>(dist[k], radius) : (R)1;
+        const R env = use_env ? gate_cutoff<R, FAST>(dk, radius) : (R)1;
         float eo[4], gn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const R gc = (R)gg[j] - mu[j];
             gn[j] = (float)(gc * rs[j]);                            // normalised pre-activation, saved for backward
             const R gh = gc * sc[j] + sh[j];
-            const float sig = (float)(env * sigmoid_r<R>(gh));     // the reference materialises sigma_ij in fp32
+            const float sig = (float)(env * gate_sigmoid<R, FAST>(gh));   // the reference materialises sigma_ij in fp32
             eo[j] = ee[j] + sig;                                    // cartnet.py:225
             acc[j] += (R)sig * (R)ss[j];                            // cartnet.py:259
         }
@@ -340,6 +360,26 @@ edge_gate_aggregate_kernel(const float* __restrict__ g, const T* __restrict__ s,
         *reinterpret_cast<float4*>(e_out + o) = eo4;
         if (e_out_t) store4<T>(e_out_t + o, eo4);
         if (gn_t) store4<T>(gn_t + o, make_float4(gn[0], gn[1], gn[2], gn[3]));
+    };
+    int k = k0;
+    for (; k + U <= k1; k += U) {
+        typename Raw4<T>::type g4[U], s4[U];                 // unconverted (8 bytes for bf16) until they are used
+        float4 e4[U];
+        float dk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t o = (int64_t)(k + u) * D + col;
+            g4[u] = ld_raw4<T>(g + o);
+            s4[u] = ld_raw4<T>(s + o);
+            e4[u] = __ldg(reinterpret_cast<const float4*>(e + o));
+            dk[u] = use_env ? __ldg(dist + k + u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) edge(k + u, g4[u], s4[u], e4[u], dk[u]);
+    }
+    for (; k < k1; ++k) {
+        const int64_t o = (int64_t)k * D + col;
+        edge(k, ld_raw4<T>(g + o), ld_raw4<T>(s + o), __ldg(reinterpret_cast<const float4*>(e + o)), use_env ? __ldg(dist + k) : 0.f);
     }
     *reinterpret_cast<float4*>(m + (int64_t)node * D + col) = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
 }
@@ -507,6 +547,32 @@ __global__ void edge_features_kernel(const float* __restrict__ cart_dist, const 
     store4<T>(feat + e * ld + col, make_float4(v[0], v[1], v[2], v[3]));
 }
 
+// Centre of the gate pre-activation g = H_g G2^T + bg2, so that g - center can be stored in T without losing the
+// bits BatchNorm needs (|mean(g)| is ~15 std at initialisation). Any shift within ~1 std of the true mean will do --
+// BatchNorm removes a per-column shift exactly -- so the batch mean of a row SAMPLE of H_g is used (sums over `rows`
+// sampled rows): center = G2 mean_s(H_g) + bg2, bias_c = bg2 - center. Eval mode: center = running_mean.
+__global__ void __launch_bounds__(256)
+gate_center_kernel(const float* __restrict__ hsum, int rows, const float* __restrict__ G2, const float* __restrict__ bg2,
+                   const float* __restrict__ running_mean, int training, int D, float* __restrict__ bias_c,
+                   float* __restrict__ center) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // one warp per output channel
+    const int lane = threadIdx.x & 31;
+    if (j >= D) return;
+    if (!training) {
+        if (lane == 0) { center[j] = running_mean[j]; bias_c[j] = bg2[j] - running_mean[j]; }
+        return;
+    }
+    float acc = 0.f;
+    for (int k = lane; k < D; k += 32) acc = fmaf(G2[(int64_t)j * D + k], hsum[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float mu = acc / (float)rows;
+        bias_c[j] = -mu;
+        center[j] = bg2[j] + mu;
+    }
+}
+
 static inline bool row_shape_ok(int D) {
     int tpr = D / 4;
     return D % 4 == 0 && tpr >= 1 && tpr <= 256 && (256 % tpr) == 0;
@@ -520,14 +586,38 @@ extern "C" {
 
 int64_t cartnet_colstats_workspace(int32_t C) { return (int64_t)kRedBlocksMax * 3 * C * (int64_t)sizeof(double); }
 
-int cartnet_colstats(const float* x, int64_t rows, int32_t C, int64_t ld, float* mean, float* var, float* running_mean,
-                     float* running_var, float momentum, double* partial, cartnet_stream_t stream) {
+int cartnet_colstats(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld, const float* shift,
+                     float* mean, float* var, float* running_mean, float* running_var, float momentum, double* partial,
+                     cartnet_stream_t stream) {
     CN_CHECK_ARG(x && mean && var && partial && rows > 0, "colstats: bad arguments");
     CN_CHECK_ARG(colreduce_shape_ok(C) && ld % 4 == 0, "colstats: C/4 must be a power of two <= 256 (C=%d)", C);
     CN_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "colstats: running stats must come in pairs");
-    StatsF f{x, ld};
-    return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0,
-                         (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_is_t && prec == CARTNET_PREC_BF16) {
+        StatsF<__nv_bfloat16> f{(const __nv_bfloat16*)x, ld};
+        return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0, st, shift);
+    }
+    StatsF<float> f{(const float*)x, ld};
+    return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0, st, shift);
+}
+
+int cartnet_gate_center(const void* H_g, int64_t ldh, int64_t num_edges, int32_t D, const float* G2, const float* bg2,
+                        const float* running_mean, int32_t training, int32_t prec, float* bias_c, float* center,
+                        float* hsum, double* partial, cartnet_stream_t stream) {
+    CN_CHECK_ARG(G2 && bg2 && bias_c && center && D > 0, "gate_center: null pointer");
+    CN_CHECK_ARG(training || running_mean, "gate_center: eval mode needs running_mean");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rows = 0;
+    if (training) {
+        CN_CHECK_ARG(H_g && hsum && partial && num_edges > 0, "gate_center: training mode needs H_g, hsum, partial and edges");
+        // <= 4096 rows at a fixed stride: the sample mean is within std/64 of the batch mean
+        const int64_t step = num_edges > 4096 ? num_edges / 4096 : 1;
+        rows = (int)((num_edges + step - 1) / step);
+        if (int rc = cartnet_colsum(H_g, 1, prec, rows, D, ldh * step, hsum, partial, stream)) return rc;
+    }
+    gate_center_kernel<<<ceil_div(D, 8), 256, 0, st>>>(hsum, rows, G2, bg2, running_mean, training, D, bias_c, center);
+    CN_LAUNCH_CHECK();
+    return 0;
 }
 
 int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld, float* out,
@@ -565,25 +655,25 @@ int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const f
     return 0;
 }
 
-int cartnet_edge_gate_aggregate(const float* g, const void* s_t, const float* e, const float* dist,
+int cartnet_edge_gate_aggregate(const void* g_t, const void* s_t, const float* e, const float* dist,
                                 const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
                                 const float* bn_mean, const float* bn_var, const float* bn_weight, const float* bn_bias,
                                 float eps, float radius, int32_t use_envelope, float* e_out, void* e_out_t, void* gn_t,
                                 int32_t prec, float* m, cartnet_stream_t stream) {
-    CN_CHECK_ARG(row_ptr && bn_mean && bn_var && m, "edge_gate_aggregate: null pointer");
-    CN_CHECK_ARG(num_edges == 0 || (g && s_t && e && dist && e_out), "edge_gate_aggregate: null edge tensor");
+    CN_CHECK_ARG(row_ptr && bn_var && m, "edge_gate_aggregate: null pointer");
+    CN_CHECK_ARG(num_edges == 0 || (g_t && s_t && e && dist && e_out), "edge_gate_aggregate: null edge tensor");
     CN_CHECK_ARG(row_shape_ok(D), "edge_gate_aggregate: unsupported D=%d", D);
     if (num_nodes <= 0) return 0;
     const int npb = 256 / (D / 4);
     if (prec == CARTNET_PREC_FP32) {
-        edge_gate_aggregate_kernel<float, double><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
-            g, (const float*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-            e_out, (float*)e_out_t, (float*)gn_t, m);
+        edge_gate_aggregate_kernel<float, double, false><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
+            (const float*)g_t, (const float*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius,
+            use_envelope, e_out, (float*)e_out_t, (float*)gn_t, m);
     } else {
         CN_DISPATCH_PREC(prec, {
-            edge_gate_aggregate_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
-                g, (const T*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius, use_envelope,
-                e_out, (T*)e_out_t, (T*)gn_t, m);
+            edge_gate_aggregate_kernel<T, float, true><<<ceil_div(num_nodes, npb), 256, 0, (cudaStream_t)stream>>>(
+                (const T*)g_t, (const T*)s_t, e, dist, row_ptr, num_nodes, D, bn_mean, bn_var, bn_weight, bn_bias, eps, radius,
+                use_envelope, e_out, (T*)e_out_t, (T*)gn_t, m);
         });
     }
     CN_LAUNCH_CHECK();

@@ -7,7 +7,7 @@
 
 namespace cartnet {
 
-int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st);   // bf16 or tf32 by d.prec                                  // gemm_tc.cu
+int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats = nullptr, int* stats_blocks = nullptr);   // bf16 or tf32 by d.prec                                  // gemm_tc.cu
 int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, const TnDst& C,
                int64_t ldc, float* ws, int64_t ws_bytes, cudaStream_t st);                 // gemm_tc.cu
 int64_t gemm_tc_tn_workspace(int prec, int M, int N, int64_t K);
@@ -182,6 +182,24 @@ int cartnet_gemm(const cartnet_gemm_t* d, cartnet_stream_t stream) {
                                                              n_tiles, (int64_t)d->K);
     CN_LAUNCH_CHECK();
     return 0;
+}
+
+int cartnet_gemm_colstats(const cartnet_gemm_t* d, const float* shift, float* mean, float* var, float* running_mean,
+                          float* running_var, float momentum, double* partial, cartnet_stream_t stream) {
+    CN_CHECK_ARG(d && d->out_t && !d->out_f32 && !d->z_out && d->act == CARTNET_ACT_NONE && !d->gather0 && !d->gather1 && !d->resid,
+                 "gemm_colstats: only the bias + T-output epilogue is supported");
+    CN_CHECK_ARG(mean && var && partial && d->M > 0, "gemm_colstats: bad arguments");
+    CN_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "gemm_colstats: running stats must come in pairs");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->prec == CARTNET_PREC_BF16 || d->prec == CARTNET_PREC_TF32) {
+        CN_CHECK_ARG(d->A && d->B && d->bias && d->N > 0 && d->K > 0, "gemm_colstats: bad GEMM arguments");
+        int blocks = 0;
+        if (int rc = gemm_tc_nt(*d, st, partial, &blocks)) return rc;       // sums ride in the epilogue
+        return launch_colstats_final(partial, blocks, d->N, d->M, shift, mean, var, running_mean, running_var, momentum, st);
+    }
+    // fp32 parity mode: SIMT GEMM, then the fp64 statistics pass over its output
+    if (int rc = cartnet_gemm(d, stream)) return rc;
+    return cartnet_colstats(d->out_t, 1, d->prec, d->M, d->N, d->ldt, shift, mean, var, running_mean, running_var, momentum, partial, stream);
 }
 
 int64_t cartnet_gemm_tn_workspace(int32_t prec, int32_t M, int32_t N, int64_t K) {

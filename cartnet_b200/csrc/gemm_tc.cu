@@ -153,7 +153,8 @@ struct TcTraits<tf32_t> {
 // The epilogue is the critical path of these GEMMs (K is only 256..1024), so it is specialised at compile time
 // per use-site: EPI is a bit mask of the steps of cartnet_gemm_t that are present; EPI_GENERIC keeps the
 // runtime-checked version for any other combination.
-enum : int { EB_BIAS = 1, EB_GATHER = 2, EB_ZOUT = 4, EB_SILU = 8, EB_DSILU = 16, EB_RESID = 32, EB_OUTF = 64, EB_OUTT = 128 };
+enum : int { EB_BIAS = 1, EB_GATHER = 2, EB_ZOUT = 4, EB_SILU = 8, EB_DSILU = 16, EB_RESID = 32, EB_OUTF = 64, EB_OUTT = 128,
+              EB_STATS = 256 };   // EB_STATS: per-column sum / sum of squares of the output rides in the epilogue (BatchNorm statistics)
 constexpr int EPI_GENERIC = -1;
 
 // sigmoid(v) = 0.5 tanh(v/2) + 0.5: ONE MUFU op (tanh.approx, ~2^-11 rel. error -- below the bf16 / tf32 operand
@@ -175,24 +176,9 @@ __device__ __forceinline__ float dsilu_fast(float z) {
 template <int EPI>
 __host__ __device__ constexpr bool epi_has(int bit, bool runtime) { return EPI == EPI_GENERIC ? runtime : ((EPI & bit) != 0); }
 
-// raw (unconverted) 4-element loads so that all global reads of a chunk can be issued before any math / store
-template <typename T> struct Raw4;
-template <> struct Raw4<tf32_t> { using type = float4; };
-template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
-template <typename T> __device__ __forceinline__ typename Raw4<T>::type ld_raw4(const T* p);
-template <> __device__ __forceinline__ float4 ld_raw4<tf32_t>(const tf32_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-template <> __device__ __forceinline__ uint2 ld_raw4<__nv_bfloat16>(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-__device__ __forceinline__ float4 cvt_raw4(const float4& r) { return r; }
-__device__ __forceinline__ float4 cvt_raw4(const uint2& r) {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
-    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
-    return make_float4(fa.x, fa.y, fb.x, fb.y);
-}
-
 // one float4 (4 consecutive columns) of one output row; inputs were loaded beforehand, outputs point at [row, col]
 template <typename T, int EPI>
-__device__ __forceinline__ void epi_tc4(const EpiParams<T>& p, float4 v, const float4& bias4, bool has_g0, bool has_g1,
+__device__ __forceinline__ float4 epi_tc4(const EpiParams<T>& p, float4 v, const float4& bias4, bool has_g0, bool has_g1,
                                         const float4& ga, const float4& gb, const float4& z, const float4& rs, T* z_out,
                                         float* out_f32, T* out_t) {
     if (epi_has<EPI>(EB_BIAS, p.bias != nullptr)) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
@@ -208,6 +194,27 @@ __device__ __forceinline__ void epi_tc4(const EpiParams<T>& p, float4 v, const f
     if (epi_has<EPI>(EB_RESID, p.resid != nullptr)) { v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w; }
     if (epi_has<EPI>(EB_OUTF, p.out_f32 != nullptr)) *reinterpret_cast<float4*>(out_f32) = v;
     if (epi_has<EPI>(EB_OUTT, p.out_t != nullptr)) store4<T>(out_t, v);
+    return v;
+}
+
+// The 4 row groups of a warp (lane >> 3) hold partial column sums of the same 4 columns: combine them with a fixed
+// butterfly, then the owner lane (lane < 8) adds the 32-row block sums to the warp's running totals in shared memory.
+__device__ __forceinline__ void stats_flush(float* wstat, int cidx, int lane, float4 ss, float4 sq) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+        ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+        sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+        sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+    }
+    if (lane < 8) {
+        float4* a = reinterpret_cast<float4*>(wstat + cidx);
+        float4* b = reinterpret_cast<float4*>(wstat + 128 + cidx);
+        float4 va = *a, vb = *b;
+        va.x += ss.x; va.y += ss.y; va.z += ss.z; va.w += ss.w;
+        vb.x += sq.x; vb.y += sq.y; vb.z += sq.z; vb.w += sq.w;
+        *a = va; *b = vb;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ NT kernel
@@ -222,11 +229,12 @@ struct NtBars {
     uint64_t a_full[NT_STAGES], a_empty[NT_STAGES], b_full, tmem_full[2], tmem_empty[2];
     uint32_t tmem_slot;
 };
+constexpr int NT_STAT_BYTES = NT_EPI_WARPS * 2 * 128 * 4;          // per-warp [sum | sumsq][<= 128 columns] (EB_STATS only)
 
 template <typename T, int EPI>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-             int BN, int n_tiles, int m_tiles, EpiParams<T> epi) {
+             int BN, int n_tiles, int m_tiles, EpiParams<T> epi, double* __restrict__ stats) {
     using TR = TcTraits<T>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -314,6 +322,14 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c_end = (c_begin + cols_per_grp) < BN ? (c_begin + cols_per_grp) : BN;
         float* stg = smemStg + (warp - 2) * 32 * NT_STG_PITCH;
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        // EB_STATS: this warp's running column sums over all of its tiles (fp32; the caller centres the output so that
+        // |mean| <~ std), one owner lane per column -> fixed order, no atomics; written out as fp64 partials at the end
+        float* wstat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(NtBars) + 15) & ~(size_t)15)) + (warp - 2) * 256;
+        constexpr bool kStats = EPI != EPI_GENERIC && (EPI & EB_STATS) != 0;
+        if (kStats) {
+            for (int i = lane; i < 256; i += 32) wstat[i] = 0.f;
+            __syncwarp();
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles; mt += m_stride) {
@@ -364,14 +380,20 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if (has_z) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
                         if (has_r) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
                     }
+                    float4 ss = zero, sq = zero;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int64_t row = row0 + it * 4 + sub_r;
-                        epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
-                                        has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
-                                        epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
-                                        epi.out_t + row * epi.ldt + col);
+                        const float4 o = epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
+                                                         has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
+                                                         epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
+                                                         epi.out_t + row * epi.ldt + col);
+                        if (kStats) {
+                            ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
+                            sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
+                        }
                     }
+                    if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);
                 } else {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
@@ -382,16 +404,22 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
                         if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
                     }
+                    float4 ss = zero, sq = zero;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int64_t row = row0 + it * 4 + sub_r;
                         if (row < M) {
-                            epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
-                                            has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
-                                            epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
-                                            epi.out_t + row * epi.ldt + col);
+                            const float4 o = epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
+                                                             has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
+                                                             epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
+                                                             epi.out_t + row * epi.ldt + col);
+                            if (kStats) {
+                                ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
+                                sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
+                            }
                         }
                     }
+                    if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
                 }
             }
             tc_fence_before();
@@ -399,6 +427,15 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if (kStats) {
+            // one partial row per (m-CTA, TMEM lane quarter): [blk][sum | sumsq][N] fp64, summed in a fixed order afterwards
+            __syncwarp();
+            const int64_t blk = (int64_t)(blockIdx.x / n_tiles) * 4 + q;
+            for (int i = lane; i < c_end - c_begin; i += 32) {
+                stats[(blk * 2 + 0) * N + n0 + c_begin + i] = (double)wstat[i];
+                stats[(blk * 2 + 1) * N + n0 + c_begin + i] = (double)wstat[128 + i];
+            }
         }
     }
     tc_fence_before();
@@ -563,7 +600,7 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const v
 }
 
 template <typename T>
-static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
+static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks) {
     using TR = TcTraits<T>;
     const int esize = (int)sizeof(T);
     CN_CHECK_ARG(d.K % TR::KB == 0, "tcgen05 gemm: K=%d must be a multiple of %d", d.K, TR::KB);
@@ -581,8 +618,11 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     if (rc) return rc;
     rc = make_map(&tmB, TR::DT, esize, d.B, d.N, d.K, d.ldb, TR::KB, BN);
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64;
+    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
+                        (stats ? NT_STAT_BYTES : 0);
+    if (stats_blocks) *stats_blocks = (grid / n_tiles) * 4;
     int mask = 0;
+    if (stats) mask |= EB_STATS;
     if (d.bias) mask |= EB_BIAS;
     if (d.gather0 && d.gather1) mask |= EB_GATHER;
     if (d.z_out) mask |= EB_ZOUT;
@@ -597,7 +637,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     if (mask == (M_)) {                                                                                              \
         static bool attr_done[64] = {};                                                                              \
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_)>, attr_done)) return rc_;                                 \
-        tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);   \
+        tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi, stats); \
         CN_LAUNCH_CHECK();                                                                                           \
         return 0;                                                                                                    \
     }
@@ -605,6 +645,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     CN_NT_CASE(EB_BIAS | EB_GATHER | EB_ZOUT | EB_SILU | EB_OUTT)         // first Linear of both MLPs (per edge)
     CN_NT_CASE(EB_BIAS | EB_OUTF)                                         // second Linear of MLP_gate -> g (fp32: BatchNorm input)
     CN_NT_CASE(EB_BIAS | EB_OUTT)                                         // second Linear of MLP_aggr -> s (T)
+    CN_NT_CASE(EB_BIAS | EB_OUTT | EB_STATS)                              // second Linear of MLP_gate -> centred g (T) + BatchNorm sums
     CN_NT_CASE(EB_DSILU | EB_OUTT)                                        // dgrad through the second Linears
     CN_NT_CASE(EB_RESID | EB_OUTF)                                        // dgrad to e / x with the residual
     CN_NT_CASE(EB_OUTF)                                                   // dgrad to e when no gradient enters e_out (last layer)
@@ -612,18 +653,20 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st) {
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF | EB_OUTT)           // edge encoder, second Linear (bf16)
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF)                     // edge encoder, second Linear (tf32)
 #undef CN_NT_CASE
+    CN_CHECK_ARG(!stats, "tcgen05 gemm: fused column statistics need the bias + T-output epilogue");
     {
         static bool attr_done[64] = {};
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, EPI_GENERIC>, attr_done)) return rc_;
-        tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi);
+        tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi, nullptr);
         CN_LAUNCH_CHECK();
     }
     return 0;
 }
 
-int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st) {
-    if (d.prec == CARTNET_PREC_BF16) return run_nt<__nv_bfloat16>(d, st);
-    return run_nt<tf32_t>(d, st);
+// stats: optional fp64 partial buffer [stats_blocks][2][N] (sum | sum of squares of the output columns)
+int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks) {
+    if (d.prec == CARTNET_PREC_BF16) return run_nt<__nv_bfloat16>(d, st, stats, stats_blocks);
+    return run_nt<tf32_t>(d, st, stats, stats_blocks);
 }
 
 struct TnPlan {

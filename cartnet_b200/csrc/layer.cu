@@ -125,23 +125,27 @@ int cartnet_layer_fwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         d.out_t = L->H; d.ldt = 2 * D;
         CN_TRY(cartnet_gemm(&d, st));
         // second Linears                                                             (cartnet.py:190,195)
+        // g is stored centred (g - center, T): BatchNorm removes the shift, the bits go to the part it keeps
+        CN_TRY(cartnet_gate_center(L->H, 2 * D, E, D, L->G2, L->bg2, L->bn1_rm, L->training, prec, L->bias_c, L->center, L->hsum,
+                                   L->partial, st));
         cartnet_gemm_t dg = gemm_desc(prec, (int)E, D, D, L->H, 2 * D, L->G2_t, D);
-        dg.bias = L->bg2; dg.out_f32 = L->g; dg.ldo = D;
-        CN_TRY(cartnet_gemm(&dg, st));
+        dg.bias = L->bias_c; dg.out_t = L->g_t; dg.ldt = D;
+        if (L->training) {
+            // edge BatchNorm statistics (global barrier over E rows, cartnet.py:238) ride in this GEMM's epilogue
+            CN_TRY(cartnet_gemm_colstats(&dg, L->center, L->mean1, L->var1, L->bn1_rm, L->bn1_rv, L->momentum1, L->partial, st));
+        } else {
+            CN_TRY(cartnet_gemm(&dg, st));
+        }
         cartnet_gemm_t ds = gemm_desc(prec, (int)E, D, D, toff((const void*)L->H, prec, D), 2 * D, L->A2_t, D);
         ds.bias = L->ba2; ds.out_t = L->s_t; ds.ldt = D;
         CN_TRY(cartnet_gemm(&ds, st));
     }
-    // edge BatchNorm statistics (global barrier over E rows)                         (cartnet.py:238)
-    const float *mean1 = L->bn1_rm, *var1 = L->bn1_rv, *mean2 = L->bn2_rm, *var2 = L->bn2_rv;
-    if (L->training) {
-        CN_TRY(cartnet_colstats(L->g, E, D, D, L->mean1, L->var1, L->bn1_rm, L->bn1_rv, L->momentum1, L->partial, st));
-        mean1 = L->mean1; var1 = L->var1;
-    }
-    CN_TRY(cartnet_edge_gate_aggregate(L->g, L->s_t, L->e, L->dist, L->row_ptr, N, E, D, mean1, var1, L->bn1_w, L->bn1_b, L->eps,
+    const float *mean1 = nullptr, *var1 = L->bn1_rv, *mean2 = L->bn2_rm, *var2 = L->bn2_rv;   // eval: g_t is centred on bn1_rm
+    if (L->training) { mean1 = L->mean1; var1 = L->var1; }
+    CN_TRY(cartnet_edge_gate_aggregate(L->g_t, L->s_t, L->e, L->dist, L->row_ptr, N, E, D, mean1, var1, L->bn1_w, L->bn1_b, L->eps,
                                        L->radius, L->use_envelope, L->e_out, L->e_out_t, L->gn_t, prec, L->m, st));
     if (L->training) {
-        CN_TRY(cartnet_colstats(L->m, N, D, D, L->mean2, L->var2, L->bn2_rm, L->bn2_rv, L->momentum2, L->partial, st));
+        CN_TRY(cartnet_colstats(L->m, 0, prec, N, D, D, nullptr, L->mean2, L->var2, L->bn2_rm, L->bn2_rv, L->momentum2, L->partial, st));
         mean2 = L->mean2; var2 = L->var2;
     }
     return cartnet_node_update(L->m, L->x, N, D, mean2, var2, L->bn2_w, L->bn2_b, L->eps, L->x_out, L->x_out_t, prec, st);   // cartnet.py:269,223

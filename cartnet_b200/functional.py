@@ -112,15 +112,19 @@ class _LayerFn(torch.autograd.Function):
         ops.gemm(prec, e_t, W1e_t, bias=b1.detach(), gather0=P[:, :2 * D], gidx0=plan.dst32,
                  gather1=P[:, 2 * D:], gidx1=plan.src32, z_out=Z, act=ACT_SILU, out_t=H)
         # second Linears                                                              (cartnet.py:190,195)
-        g = torch.empty(E, D, dtype=torch.float32, device=dev)      # BatchNorm input: fp32, scratch after this pass
+        # g is stored centred (g - center) in T: BatchNorm removes the shift, the bits go to the part it keeps
+        g = torch.empty(E, D, dtype=T, device=dev)                  # scratch after this pass
         s = torch.empty(E, D, dtype=T, device=dev)
-        ops.gemm(prec, H[:, :D], G2_t, bias=bg2.detach(), out_f32=g)
-        ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_t=s)
-        # edge BatchNorm statistics (global barrier over E rows)                      (cartnet.py:238)
-        if training:
-            mean1, var1 = ops.colstats(g, cfg["rm1"], cfg["rv1"], cfg["momentum1"])
-        else:
-            mean1, var1 = cfg["rm1"], cfg["rv1"]
+        mean1, var1 = None, cfg["rv1"]                              # eval: g is centred on the running mean
+        if E > 0:
+            bias_c, center = ops.gate_center(H[:, :D], G2.detach(), bg2.detach(), cfg["rm1"], training, prec)
+            if training:
+                # edge BatchNorm statistics (global barrier over E rows, cartnet.py:238) come with the GEMM
+                mean1, var1 = ops.gemm_colstats(prec, H[:, :D], G2_t, bias_c, g, cfg["rm1"], cfg["rv1"], cfg["momentum1"],
+                                                shift=center)
+            else:
+                ops.gemm(prec, H[:, :D], G2_t, bias=bias_c, out_t=g)
+            ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_t=s)
         e_out, e_out_t, m, gn = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
                                                         b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True)
         if training:
@@ -130,14 +134,14 @@ class _LayerFn(torch.autograd.Function):
         x_out, x_out_t = ops.node_update(m, x, mean2, var2, w2.detach(), b2n.detach(), prec, True)   # cartnet.py:269,223
         cfg["holder"]["x_t"], cfg["holder"]["e_t"] = x_out_t, e_out_t
 
-        ctx.save_for_backward(x_t, e_t, Z, H, gn, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
+        ctx.save_for_backward(x_t, e_t, Z, H, gn, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
         ctx.cfg = dict(prec=prec, plan=plan, dist=dist, training=training, radius=cfg["radius"],
                        use_envelope=cfg["use_envelope"])
         return x_out, e_out
 
     @staticmethod
     def backward(ctx, dx_out, de_out):
-        (x_t, e_t, Z, H, gn, s, m, mean1, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n) = ctx.saved_tensors
+        (x_t, e_t, Z, H, gn, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n) = ctx.saved_tensors
         c = ctx.cfg
         prec, plan, training = c["prec"], c["plan"], c["training"]
         T = t_dtype(prec)
@@ -237,13 +241,13 @@ class _NativeLayerFn(torch.autograd.Function):
             e_t = ops.cast(e, prec)
         shadow = needs_shadow(prec)
         DD = D * D
+        g_t = torch.empty(E, D, dtype=T, device=dev)                 # centred gate pre-activation; not kept for backward
         tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D + 2 * E * D, dtype=T, device=dev)
         (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H, s_t, gn_t) = _carve(tbuf, [
             (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D),
             (E, D), (E, D)])
-        g = torch.empty(E, D, dtype=torch.float32, device=dev)       # BatchNorm input; not kept for backward
-        fbuf = torch.empty(N * D + 6 * D, dtype=torch.float32, device=dev)
-        m, mean1, var1, mean2, var2, b1 = _carve(fbuf, [(N, D), (D,), (D,), (D,), (D,), (2 * D,)])
+        fbuf = torch.empty(N * D + 9 * D, dtype=torch.float32, device=dev)
+        m, mean1, var1, mean2, var2, b1, center, bias_c, hsum = _carve(fbuf, [(N, D), (D,), (D,), (D,), (D,), (2 * D,), (D,), (D,), (D,)])
         x_out = torch.empty(N, D, dtype=torch.float32, device=dev)
         e_out = torch.empty(E, D, dtype=torch.float32, device=dev)
         x_out_t = torch.empty(N, D, dtype=T, device=dev) if shadow else None
@@ -261,7 +265,7 @@ class _NativeLayerFn(torch.autograd.Function):
             setattr(L, k, p(v.detach()))
         L.bn1_rm, L.bn1_rv, L.bn2_rm, L.bn2_rv = p(cfg["rm1"]), p(cfg["rv1"]), p(cfg["rm2"]), p(cfg["rv2"])
         for k, v in dict(W1n_t=W1n_t, W1e_t=W1e_t, G2_t=G2_t, A2_t=A2_t, W1nT_t=W1nT_t, W1eT_t=W1eT_t, G2T_t=G2T_t, A2T_t=A2T_t,
-                         b1=b1, P=P, Z=Z, H=H, g=g, s_t=s_t, gn_t=gn_t, m=m, mean1=mean1, var1=var1, mean2=mean2, var2=var2, x_out=x_out,
+                         b1=b1, P=P, Z=Z, H=H, g_t=g_t, center=center, bias_c=bias_c, hsum=hsum, s_t=s_t, gn_t=gn_t, m=m, mean1=mean1, var1=var1, mean2=mean2, var2=var2, x_out=x_out,
                          e_out=e_out, x_out_t=x_out_t, e_out_t=e_out_t, partial=part).items():
             setattr(L, k, p(v))
         st = ops._stream()

@@ -250,6 +250,29 @@ def gemm(prec: int, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, 
     _lib.check(lib.cartnet_gemm(C.byref(d), _stream()), "gemm")
 
 
+def gemm_colstats(prec: int, A, B, bias, out_t, running_mean=None, running_var=None, momentum: float = 0.1, shift=None):
+    """out_t = (T)(A @ B^T + bias) together with the column mean / biased variance of that output over the M rows
+    (BatchNorm batch statistics; running buffers updated in place, `shift` as in colstats). Tensor-core modes
+    accumulate the sums in the GEMM epilogue, fp32 mode runs the statistics pass after the GEMM."""
+    lib = _lib.load()
+    T = t_dtype(prec)
+    _req(A, T, "A"); _req(B, T, "B"); _req(out_t, T, "out_t"); _req(bias, torch.float32, "bias")
+    M, K, N = int(A.shape[0]), int(A.shape[1]), int(B.shape[0])
+    if int(B.shape[1]) != K or tuple(out_t.shape) != (M, N):
+        raise ValueError("gemm_colstats: shape mismatch")
+    d = _lib.GemmDesc()
+    d.prec, d.M, d.N, d.K = prec, M, N, K
+    d.A, d.lda, d.B, d.ldb = _p(A), _ld2(A), _p(B), _ld2(B)
+    d.bias, d.act = _p(bias), ACT_NONE
+    d.out_t, d.ldt = _p(out_t), _ld2(out_t)
+    mean = torch.empty(N, dtype=torch.float32, device=A.device)
+    var = torch.empty(N, dtype=torch.float32, device=A.device)
+    part = _partial(A.device, int(lib.cartnet_colstats_workspace(N)))
+    _lib.check(lib.cartnet_gemm_colstats(C.byref(d), _p(shift), _p(mean), _p(var), _p(running_mean), _p(running_var),
+                                         float(momentum), _p(part), _stream()), "gemm_colstats")
+    return mean, var
+
+
 def gemm_tn(prec: int, A, B, out_blocks=None) -> torch.Tensor:
     """C[M,N] fp32 = A[K,M]^T @ B[K,N] (deterministic split-K). With out_blocks = [v_0 .. v_{b-1}] (b <= 4 fp32 views
     of shape [M/b, N] sharing one row pitch) row block i of C is written into v_i instead of a fresh tensor."""
@@ -278,17 +301,33 @@ def gemm_tn(prec: int, A, B, out_blocks=None) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- reductions
-def colstats(x, running_mean=None, running_var=None, momentum: float = 0.1):
-    """Per-column mean / biased variance over rows; updates running stats in place (train-mode BN)."""
+def colstats(x, running_mean=None, running_var=None, momentum: float = 0.1, shift=None, prec: int = PREC_FP32):
+    """Per-column mean / biased variance over rows of x (fp32, or T of `prec`); updates running stats in place
+    (train-mode BN). `shift` [C]: x was stored centred (x = true - shift); only the running-mean update sees it."""
     lib = _lib.load()
-    _req(x, torch.float32, "x")
+    is_t = 0 if x.dtype == torch.float32 and prec != PREC_TF32 else 1
+    _req(x, t_dtype(prec) if is_t else torch.float32, "x")
     rows, Cc = int(x.shape[0]), int(x.shape[1])
     mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
     var = torch.empty(Cc, dtype=torch.float32, device=x.device)
     part = _partial(x.device, int(lib.cartnet_colstats_workspace(Cc)))
-    _lib.check(lib.cartnet_colstats(_p(x), rows, Cc, _ld2(x), _p(mean), _p(var), _p(running_mean), _p(running_var),
-                                    float(momentum), _p(part), _stream()), "colstats")
+    _lib.check(lib.cartnet_colstats(_p(x), is_t, prec, rows, Cc, _ld2(x), _p(shift), _p(mean), _p(var), _p(running_mean),
+                                    _p(running_var), float(momentum), _p(part), _stream()), "colstats")
     return mean, var
+
+
+def gate_center(H_g, G2, bg2, running_mean, training: bool, prec: int):
+    """(bias_c, center) for the centred gate GEMM g - center = H_g G2^T + bias_c; see cartnet_gate_center."""
+    lib = _lib.load()
+    _req(H_g, t_dtype(prec), "H_g"); _req(G2, torch.float32, "G2")
+    E, D = int(H_g.shape[0]), int(H_g.shape[1])
+    dev = H_g.device
+    out = torch.empty(3, D, dtype=torch.float32, device=dev)
+    part = _partial(dev, int(lib.cartnet_colstats_workspace(D)))
+    _lib.check(lib.cartnet_gate_center(_p(H_g), _ld2(H_g), E, D, _p(G2.contiguous()), _p(bg2), _p(running_mean),
+                                       int(bool(training)), prec, _p(out[0]), _p(out[1]), _p(out[2]), _p(part), _stream()),
+               "gate_center")
+    return out[0], out[1]
 
 
 def colsum(x, prec: int) -> torch.Tensor:
@@ -305,11 +344,11 @@ def colsum(x, prec: int) -> torch.Tensor:
 # ----------------------------------------------------------------------------- layer passes
 def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes: int, bn_mean, bn_var, bn_w, bn_b, radius: float,
                         use_envelope: bool, prec: int, want_shadow: bool, want_gn: bool = True):
-    """g fp32 (BatchNorm input), s T. Returns e_out (fp32), its T shadow, m, and gn_t = (g-mean)*rstd in T (what the
-    backward pass reads instead of g)."""
+    """g, s: T (g possibly stored centred, bn_mean = mean of the stored values, None = 0). Returns e_out (fp32), its T
+    shadow, m, and gn_t = (g-mean)*rstd in T (what the backward pass reads instead of g)."""
     lib = _lib.load()
     T = t_dtype(prec)
-    for nm, t, dt in (("g", g, torch.float32), ("s", s, T), ("e", e, torch.float32)):
+    for nm, t, dt in (("g", g, T), ("s", s, T), ("e", e, torch.float32)):
         _req(t, dt, nm)
         if not t.is_contiguous():
             raise ValueError("%s must be contiguous" % nm)

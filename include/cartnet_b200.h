@@ -152,6 +152,14 @@ int cartnet_gemm_tn(int32_t prec, int32_t M, int32_t N, int64_t K, const void* A
                     const void* B, int64_t ldb, float* C, int64_t ldc, float* workspace,
                     int64_t workspace_bytes, cartnet_stream_t stream);
 
+/* GEMM (bias + T output only) whose per-column output statistics come with it: mean/var of C's columns over the M rows
+ * as cartnet_colstats would compute them from out_t (same shift / running-statistics semantics). In the tensor-core
+ * modes the sums are accumulated in the epilogue (no extra pass over C, taken before the rounding to T); in fp32 mode
+ * the statistics pass runs after the GEMM. partial: >= cartnet_colstats_workspace(N) bytes. */
+int cartnet_gemm_colstats(const cartnet_gemm_t* d /* host */, const float* shift, float* mean, float* var,
+                          float* running_mean, float* running_var, float momentum, double* partial,
+                          cartnet_stream_t stream);
+
 /* Same, with the M output rows split into num_blocks (1..4) equal blocks that are written to separate bases
  * C_blocks[b] (host array of device pointers, each [M/num_blocks, N] with pitch ldc): the gradient of a row-packed
  * weight ([G1_e;A1_e], [G1_i;A1_i;G1_j;A1_j]) lands directly in the reference's [D,3D] parameter layout. */
@@ -164,13 +172,22 @@ int cartnet_gemm_tn_blocks(int32_t prec, int32_t M, int32_t N, int64_t K, const 
  * and over N rows (cartnet.py:199,269). Sums are accumulated in fp64 in a fixed order.
  * ------------------------------------------------------------------------------------- */
 
-/* mean[C], var[C] (biased) of x[rows, C] (fp32, ld). If running_mean/var non-null they are updated in
- * place like nn.BatchNorm1d in train mode: r = (1-momentum) r + momentum * stat, with the UNBIASED
- * variance. partial: fp64 scratch, >= cartnet_colstats_workspace(C) bytes. */
+/* mean[C], var[C] (biased) of x[rows, C] (T when x_is_t, else fp32; pitch ld). If running_mean/var non-null they are
+ * updated in place like nn.BatchNorm1d in train mode: r = (1-momentum) r + momentum * stat, with the UNBIASED
+ * variance; `shift` (nullable, [C]) is added to the mean in that update only (x was stored centred: x = true - shift).
+ * partial: fp64 scratch, >= cartnet_colstats_workspace(C) bytes. */
 int64_t cartnet_colstats_workspace(int32_t C);
-int cartnet_colstats(const float* x, int64_t rows, int32_t C, int64_t ld, float* mean, float* var,
-                     float* running_mean, float* running_var, float momentum, double* partial,
-                     cartnet_stream_t stream);
+int cartnet_colstats(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld,
+                     const float* shift, float* mean, float* var, float* running_mean, float* running_var,
+                     float momentum, double* partial, cartnet_stream_t stream);
+
+/* Centre for the gate pre-activation g = H_g G2^T + bg2 (cartnet.py:195-196) so that g - center can be stored in T:
+ * BatchNorm removes any per-column shift exactly, so an approximate mean is enough. Training: center = bg2 +
+ * G2 mean_s(H_g) over <= 4096 rows of H_g (T, pitch ldh) sampled at a fixed stride; eval: center = running_mean.
+ * Outputs bias_c = bg2 - center (the bias of the centred GEMM) and center, both [D]. hsum: [D] fp32 scratch. */
+int cartnet_gate_center(const void* H_g, int64_t ldh, int64_t num_edges, int32_t D, const float* G2,
+                        const float* bg2, const float* running_mean, int32_t training, int32_t prec,
+                        float* bias_c, float* center, float* hsum, double* partial, cartnet_stream_t stream);
 
 /* out[C] (fp32) = column sums of x[rows, C] (T or fp32 selected by x_is_t/prec). */
 int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, int32_t C, int64_t ld,
@@ -185,10 +202,11 @@ int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, in
 /* Forward edge pass:  ghat = BN(g); sig = env(dist) * sigmoid(ghat); e_out = e + sig;
  * m[i] = sum_{edges -> i, CSR order} sig * s   (deterministic, no atomics).
  * env(d) = 0.5 (cos(pi d / radius) + 1) (d < radius) when use_envelope else 1.
- * g is fp32 (BatchNorm input), s_t is T. e_out_t (T shadow for the next layer's GEMM operand) may be null.
- * gn_t (T, may be null) receives the normalised pre-activation (g - mean) * rstd: with s_t it is all the
- * backward pass needs, so g itself is scratch. */
-int cartnet_edge_gate_aggregate(const float* g, const void* s_t, const float* e, const float* dist,
+ * g_t and s_t are T; g_t may be stored centred (cartnet_gate_center) with bn_mean = the mean of the stored values
+ * (null = 0: eval mode, centred on the running mean). e_out_t (T shadow for the next layer's GEMM operand) may be
+ * null. gn_t (T, may be null) receives the normalised pre-activation (g - mean) * rstd: with s_t it is all the
+ * backward pass needs, so g_t itself is scratch. */
+int cartnet_edge_gate_aggregate(const void* g_t, const void* s_t, const float* e, const float* dist,
                                 const int32_t* row_ptr, int32_t num_nodes, int64_t num_edges, int32_t D,
                                 const float* bn_mean, const float* bn_var, const float* bn_weight,
                                 const float* bn_bias, float eps, float radius, int32_t use_envelope,
@@ -273,7 +291,9 @@ typedef struct cartnet_layer {
     float* b1;
     /* forward: saved activations and outputs */
     void *P, *Z, *H;                                 /* T: [N,4D], [E,2D], [E,2D] */
-    float *g, *m;                                    /* [E,D] (scratch after the forward pass), [N,D] */
+    void* g_t;                                       /* T [E,D]: centred gate pre-activation (scratch after the forward pass) */
+    float *center, *bias_c, *hsum;                   /* [D] each: cartnet_gate_center outputs / scratch */
+    float* m;                                        /* [N,D] */
     void *s_t, *gn_t;                                /* T [E,D]: MLP_aggr output, normalised gate pre-activation (saved) */
     float *mean1, *var1, *mean2, *var2;              /* [D] statistics used (batch or running) */
     float *x_out, *e_out;                            /* [N,D], [E,D] */

@@ -110,11 +110,17 @@ def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1
         out_t.copy_(v.to(out_t.dtype))
 
 
+def gemm_colstats(prec, A, B, bias, out_t, running_mean=None, running_var=None, momentum=0.1, shift=None):
+    v = (_f(A) @ _f(B).t() + _f(bias)).float()
+    out_t.copy_(_shadow(v, prec))
+    return colstats(v, running_mean, running_var, momentum, shift=shift)      # sums are taken before the rounding to T
+
+
 def gemm_tn(prec, A, B):
     return (_f(A).t() @ _f(B)).to(torch.float32)
 
 
-def colstats(x, running_mean=None, running_var=None, momentum=0.1):
+def colstats(x, running_mean=None, running_var=None, momentum=0.1, shift=None, prec=PREC_FP32):
     xx = x.to(torch.float64)
     n = x.shape[0]
     mean = xx.mean(0)
@@ -122,9 +128,21 @@ def colstats(x, running_mean=None, running_var=None, momentum=0.1):
     var = var.clamp(min=0)
     if running_mean is not None:
         unb = var * n / (n - 1) if n > 1 else var
-        running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * mean).float())
+        true_mean = mean if shift is None else mean + shift.double()
+        running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * true_mean).float())
         running_var.copy_(((1 - momentum) * running_var.double() + momentum * unb).float())
     return mean.float(), var.float()
+
+
+def gate_center(H_g, G2, bg2, running_mean, training, prec):
+    if not training:
+        return (bg2 - running_mean).float(), running_mean.clone()
+    E = H_g.shape[0]
+    step = E // 4096 if E > 4096 else 1
+    rows = (E + step - 1) // step
+    hsum = _f(H_g)[::step][:rows].sum(0)
+    mu = (_f(G2) @ hsum) / rows
+    return (-mu).float(), (_f(bg2) + mu).float()
 
 
 def colsum(x, prec):
@@ -133,7 +151,8 @@ def colsum(x, prec):
 
 def edge_gate_aggregate(g, s, e, dist, row_ptr, num_nodes, bn_mean, bn_var, bn_w, bn_b, radius, use_envelope, prec,
                         want_shadow, want_gn=True):
-    ghat, gn, _ = _bn(_f(g), _f(bn_mean), _f(bn_var), _f(bn_w), _f(bn_b))
+    mean = torch.zeros_like(bn_var) if bn_mean is None else bn_mean
+    ghat, gn, _ = _bn(_f(g), _f(mean), _f(bn_var), _f(bn_w), _f(bn_b))
     sig = _env(_f(dist), radius, use_envelope).unsqueeze(-1) * torch.sigmoid(ghat)
     e_out = (_f(e) + sig).float()
     counts = (row_ptr[1:] - row_ptr[:-1]).long()
@@ -194,7 +213,7 @@ def cast(x, prec):
     return _shadow(x, prec)
 
 
-ALL = ["graph_plan", "edge_features", "gemm", "gemm_tn", "colstats", "colsum", "edge_gate_aggregate", "node_update",
+ALL = ["graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
        "node_update_bwd", "edge_gate_bwd", "segment_sum", "dsilu_mul", "cast"]
 
 

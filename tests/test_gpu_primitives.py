@@ -128,6 +128,65 @@ def test_colstats_and_running_update():
     assert common.rel_err(ops.colsum(x.cuda(), PREC_FP32), x.double().sum(0).float()) < 1e-6
 
 
+@pytest.mark.parametrize("prec", PRECS + [PREC_TF32])
+def test_colstats_of_centred_T_tensor_with_shift(prec):
+    """statistics of a tensor stored centred in T (x = true - shift): mean/var are those of the stored values, the
+    running mean tracks true = stored + shift."""
+    shift = rnd(256, seed=5) * 3.0
+    x = EM.cast(rnd(20003, 256, seed=1) * 0.7 + 0.05, prec)
+    rm, rv = rnd(256, seed=2), rnd(256, seed=3).abs() + 0.5
+    rm_g, rv_g = rm.cuda(), rv.cuda()
+    mean, var = EM.colstats(x, rm, rv, 0.1, shift=shift, prec=prec)
+    mg, vg = ops.colstats(x.cuda(), rm_g, rv_g, 0.1, shift=shift.cuda(), prec=prec)
+    assert float((mg.cpu() - mean).abs().max()) < 1e-6 and common.rel_err(vg, var) < 1e-5
+    assert common.rel_err(rm_g, rm) < 1e-6 and common.rel_err(rv_g, rv) < 1e-6
+    assert common.rel_err(rm_g, 0.9 * rnd(256, seed=2) + 0.1 * (x.double().mean(0).float() + shift)) < 1e-5
+
+
+@pytest.mark.parametrize("prec", GEMM_PRECS)
+@pytest.mark.parametrize("M", [1000, 128 * 148 * 3 + 77])
+def test_gemm_colstats(prec, M):
+    """second Linear of MLP_gate with the BatchNorm sums accumulated in its epilogue (tensor-core modes) / by the
+    statistics pass (fp32 mode): output, mean, variance and running-buffer update against the specification."""
+    N = K = 256
+    T = ops.t_dtype(prec)
+    A = EM.cast(torch.nn.functional.silu(rnd(M, 2 * K, seed=1)), prec)[:, K:]          # strided view like H[:, D:]
+    B, bias, shift = EM.cast(rnd(N, K, seed=2, scale=K ** -0.5), prec), rnd(N, seed=3) * 0.1, rnd(N, seed=4)
+    rm, rv = rnd(N, seed=5), rnd(N, seed=6).abs() + 0.5
+    rm_g, rv_g = rm.cuda(), rv.cuda()
+    out = torch.empty(M, N, dtype=T)
+    mean, var = EM.gemm_colstats(prec, A, B, bias, out, rm, rv, 0.1, shift=shift)
+    Ag = EM.cast(torch.nn.functional.silu(rnd(M, 2 * K, seed=1)), prec).cuda()[:, K:]
+    outg = torch.empty(M, N, dtype=T, device="cuda")
+    mg, vg = ops.gemm_colstats(prec, Ag, B.cuda(), bias.cuda(), outg, rm_g, rv_g, 0.1, shift=shift.cuda())
+    t = {PREC_FP32: 2e-6, PREC_BF16: 8e-3, PREC_TF32: 2e-3}[prec]
+    assert common.rel_err(outg.float(), out.float()) < t
+    ts = {PREC_FP32: 2e-5, PREC_BF16: 1e-4, PREC_TF32: 2e-3}[prec]      # tensor-core modes: fp32 partial sums per warp
+    assert float((mg.cpu() - mean).abs().max()) < ts * float(var.max().sqrt()) and common.rel_err(vg, var) < ts
+    assert common.rel_err(rm_g, rm) < ts and common.rel_err(rv_g, rv) < ts
+    mg2, vg2 = ops.gemm_colstats(prec, Ag, B.cuda(), bias.cuda(), outg, None, None, 0.1)
+    assert torch.equal(mg, mg2) and torch.equal(vg, vg2)                                # deterministic reduction order
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("E", [900, 70001])
+def test_gate_center(prec, E):
+    """centre of the gate pre-activation: eval = running mean; training = bg2 + G2 mean(H_g sample), within a fraction
+    of a standard deviation of the true column mean of g (all BatchNorm needs)."""
+    D = 256
+    Hfull = EM.cast(torch.nn.functional.silu(rnd(E, 2 * D, seed=1) + 0.5), prec)
+    H = Hfull[:, :D]
+    G2, bg2, rm = rnd(D, D, seed=2, scale=D ** -0.5), rnd(D, seed=3), rnd(D, seed=4)
+    for training in (True, False):
+        ref = EM.gate_center(H, G2, bg2, rm, training, prec)
+        got = ops.gate_center(Hfull.cuda()[:, :D], G2.cuda(), bg2.cuda(), rm.cuda(), training, prec)
+        assert float((got[0].cpu() - ref[0]).abs().max()) < 1e-5 and float((got[1].cpu() - ref[1]).abs().max()) < 1e-5
+        assert float((got[0].cpu() + got[1].cpu() - bg2).abs().max()) < 1e-5          # bias_c + center = bg2
+    g = H.float() @ G2.t() + bg2
+    assert float(((got_tr := ops.gate_center(Hfull.cuda()[:, :D], G2.cuda(), bg2.cuda(), rm.cuda(), True, prec))[1].cpu()
+                  - g.mean(0)).abs().max()) < 0.25 * float(g.std(0).max())
+
+
 def _bn_args(D, seed):
     return rnd(D, seed=seed) * 0.3, rnd(D, seed=seed + 1).abs() * 0.5 + 0.2, rnd(D, seed=seed + 2) * 0.2 + 1.0, rnd(D, seed=seed + 3) * 0.2
 
@@ -145,9 +204,11 @@ def _graph(N, E, seed):
 def test_edge_gate_aggregate(prec, use_env):
     N, E, D = 301, 17011, 256
     plan = _graph(N, E, 1)
-    g, s, e = rnd(E, D, seed=1), EM.cast(rnd(E, D, seed=2), prec), rnd(E, D, seed=3)
+    g, s, e = EM.cast(rnd(E, D, seed=1), prec), EM.cast(rnd(E, D, seed=2), prec), rnd(E, D, seed=3)
     dist = torch.rand(E, generator=torch.Generator().manual_seed(4)) * 5.5
     mean, var, w, b = _bn_args(D, 5)
+    if not use_env:
+        mean = None                                        # eval mode: g arrives centred on the running mean
     ref, got = both("edge_gate_aggregate", (g, s, e, dist, plan.row_ptr, N, mean, var, w, b, 5.0, use_env, prec, True))
     tT = 2e-6 if prec == PREC_FP32 else 8e-3
     assert common.rel_err(got[0], ref[0]) < 2e-6
@@ -155,7 +216,8 @@ def test_edge_gate_aggregate(prec, use_env):
     assert common.rel_err(got[2], ref[2]) < 1e-5
     assert common.rel_err(got[3].float(), ref[3].float()) < tT          # normalised gate pre-activation saved for backward
     assert float(got[2][3].abs().max()) == 0.0             # node without in-edges gets exactly 0
-    got2 = ops.edge_gate_aggregate(g.cuda(), s.cuda(), e.cuda(), dist.cuda(), plan.row_ptr.cuda(), N, mean.cuda(), var.cuda(),
+    got2 = ops.edge_gate_aggregate(g.cuda(), s.cuda(), e.cuda(), dist.cuda(), plan.row_ptr.cuda(), N,
+                                   None if mean is None else mean.cuda(), var.cuda(),
                                    w.cuda(), b.cuda(), 5.0, use_env, prec, True, want_gn=False)
     assert torch.equal(got2[2], got[2]) and got2[3] is None   # deterministic reduction; gn is optional
 
