@@ -493,6 +493,48 @@ segment_sum_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restri
     store4<TO>(out + (int64_t)node * ldo + col, acc);
 }
 
+// Both transposed lifts in one pass: out[n, 0:C] = sum over the dst-CSR row of n of x[k, :], out[n, C:2C] = sum over the
+// src-CSR row of n of x[perm[k], :]. Every row of x is wanted twice, once through each CSR; the edges that leave n end
+// at n's neighbours, i.e. inside the same crystal, so while a block of nodes is being processed the second read of a
+// row finds it in L2 (a crystal's rows are ~10 MB) instead of HBM, which two separate launches over [E, C] cannot.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+segment_sum_pair_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ perm, int num_nodes, int C,
+                        TO* __restrict__ out, int64_t ldo) {
+    constexpr int U = 4;
+    const int tpr = C >> 2, npb = 256 / tpr;
+    const int node = blockIdx.x * npb + threadIdx.x / tpr;
+    const int col = (threadIdx.x % tpr) * 4;
+    if (node >= num_nodes) return;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t* ptr = pass ? col_ptr : row_ptr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k0 = ptr[node], k1 = ptr[node + 1];
+        int k = k0;
+        for (; k + U <= k1; k += U) {
+            typename Raw4<T>::type v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t r = pass ? (int64_t)__ldg(perm + k + u) : (int64_t)(k + u);
+                v[u] = ld_raw4<T>(x + r * ldx + col);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float4 f = cvt_raw4(v[u]);
+                acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+            }
+        }
+        for (; k < k1; ++k) {
+            const int64_t r = pass ? (int64_t)__ldg(perm + k) : (int64_t)k;
+            const float4 f = cvt_raw4(ld_raw4<T>(x + r * ldx + col));
+            acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+        }
+        store4<TO>(out + (int64_t)node * ldo + pass * C + col, acc);
+    }
+}
+
 template <typename T>
 __global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, const T* __restrict__ z, int64_t ldz,
                                  T* __restrict__ y, int64_t ldy, int64_t rows, int C) {
@@ -775,6 +817,24 @@ int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const in
             segment_sum_kernel<T, T><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, ptr, perm, num_nodes, C, (T*)out, ldo);
         else
             segment_sum_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, ptr, perm, num_nodes, C, (float*)out, ldo);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_segment_sum_pair(const void* x, int64_t ldx, const int32_t* row_ptr, const int32_t* col_ptr,
+                             const int32_t* perm_src, int32_t num_nodes, int32_t C, void* out, int64_t ldo,
+                             int32_t out_is_t, int32_t prec, cartnet_stream_t stream) {
+    CN_CHECK_ARG(row_ptr && col_ptr && perm_src && out && (x || num_nodes == 0), "segment_sum_pair: null pointer");
+    CN_CHECK_ARG(row_shape_ok(C) && ldx % 4 == 0 && ldo % 4 == 0 && ldo >= 2 * (int64_t)C, "segment_sum_pair: unsupported C=%d", C);
+    if (num_nodes <= 0) return 0;
+    const int npb = 256 / (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    CN_DISPATCH_PREC(prec, {
+        if (out_is_t)
+            segment_sum_pair_kernel<T, T><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, row_ptr, col_ptr, perm_src, num_nodes, C, (T*)out, ldo);
+        else
+            segment_sum_pair_kernel<T, float><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, row_ptr, col_ptr, perm_src, num_nodes, C, (float*)out, ldo);
     });
     CN_LAUNCH_CHECK();
     return 0;

@@ -191,8 +191,7 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         CN_TRY(cartnet_gemm_tn_blocks(prec, 2 * D, D, E, L->dZ, 2 * D, L->e_t, D, blocks, 2, 3 * D, L->splitk, L->splitk_bytes, st));
     }
     // first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
-    CN_TRY(cartnet_segment_sum(L->dZ, 2 * D, L->row_ptr, nullptr, N, 2 * D, L->dP, 4 * D, 1, prec, st));
-    CN_TRY(cartnet_segment_sum(L->dZ, 2 * D, L->col_ptr, L->perm_src, N, 2 * D, toff(L->dP, prec, 2 * D), 4 * D, 1, prec, st));
+    CN_TRY(cartnet_segment_sum_pair(L->dZ, 2 * D, L->row_ptr, L->col_ptr, L->perm_src, N, 2 * D, L->dP, 4 * D, 1, prec, st));
     // d(b1) = sum_e dZ = column sums of d(P_dst) over N rows; [0:D] -> dbg1, [D:2D] -> dba1
     CN_TRY(cartnet_colsum(L->dP, 1, prec, N, D, 4 * D, L->dbg1, L->partial, st));
     CN_TRY(cartnet_colsum(toff((const void*)L->dP, prec, D), 1, prec, N, D, 4 * D, L->dba1, L->partial, st));

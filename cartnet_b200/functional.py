@@ -180,8 +180,7 @@ class _LayerFn(torch.autograd.Function):
         dW1e = ops.gemm_tn(prec, dZ, e_t)
         # first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
         dP = torch.empty(N, 4 * D, dtype=T, device=dev)
-        ops.segment_sum(dZ, plan.row_ptr, None, N, dP[:, :2 * D], prec)
-        ops.segment_sum(dZ, plan.col_ptr, plan.perm_src, N, dP[:, 2 * D:], prec)
+        ops.segment_sum_pair(dZ, plan.row_ptr, plan.col_ptr, plan.perm_src, N, dP, prec)
         # sum_e dZ = sum_n (sum_{e -> n} dZ): N rows instead of E (two D-wide reductions, as in csrc/layer.cu)
         db1 = torch.cat([ops.colsum(dP[:, :D], prec), ops.colsum(dP[:, D:2 * D], prec)])
         dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)

@@ -429,6 +429,20 @@ def segment_sum(x, ptr, perm, num_nodes: int, out, prec: int):
     return out
 
 
+def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes: int, out, prec: int):
+    """out[:, :C] = dst-CSR segment sum of x, out[:, C:2C] = src-CSR segment sum (through perm_src), one launch;
+    `out` is a caller-provided [N, 2C] tensor (T or fp32)."""
+    lib = _lib.load()
+    _req(x, t_dtype(prec), "x")
+    Cc = int(x.shape[1])
+    if tuple(out.shape) != (num_nodes, 2 * Cc):
+        raise ValueError("segment_sum_pair: out must be [N, 2C]")
+    out_is_t = 0 if (out.dtype == torch.float32 and not f32_storage(prec)) else 1
+    _lib.check(lib.cartnet_segment_sum_pair(_p(x), _ld2(x), _p(row_ptr), _p(col_ptr), _p(perm_src), num_nodes, Cc, _p(out),
+                                            _ld2(out), out_is_t, prec, _stream()), "segment_sum_pair")
+    return out
+
+
 def dsilu_mul(dy, z, prec: int) -> torch.Tensor:
     lib = _lib.load()
     _req(dy, torch.float32, "dy"); _req(z, t_dtype(prec), "z")

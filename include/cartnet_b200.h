@@ -255,6 +255,12 @@ int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const in
                         int32_t num_nodes, int32_t C, void* out, int64_t ldo, int32_t out_is_t,
                         int32_t prec, cartnet_stream_t stream);
 
+/* Both transposed lifts in one launch: out[n, 0:C] = dst-CSR (row_ptr, identity order) sum, out[n, C:2C] = src-CSR
+ * (col_ptr through perm_src) sum of the same x. The second read of each row of x is served by L2 (see the kernel). */
+int cartnet_segment_sum_pair(const void* x, int64_t ldx, const int32_t* row_ptr, const int32_t* col_ptr,
+                             const int32_t* perm_src, int32_t num_nodes, int32_t C, void* out, int64_t ldo,
+                             int32_t out_is_t, int32_t prec, cartnet_stream_t stream);
+
 /* y_t = (T)(dy * silu'(z)) elementwise over [rows, C]; dy fp32 (ld_dy), z T (ldz), y T (ldy). */
 int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy,
                       int64_t rows, int32_t C, int32_t prec, cartnet_stream_t stream);

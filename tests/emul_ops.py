@@ -205,6 +205,13 @@ def segment_sum(x, ptr, perm, num_nodes, out, prec):
     return out
 
 
+def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes, out, prec):
+    C = x.shape[1]
+    segment_sum(x, row_ptr, None, num_nodes, out[:, :C], prec)
+    segment_sum(x, col_ptr, perm_src, num_nodes, out[:, C:], prec)
+    return out
+
+
 def dsilu_mul(dy, z, prec):
     return (_f(dy) * _dsilu(_f(z))).to(t_dtype(prec))
 
@@ -214,7 +221,7 @@ def cast(x, prec):
 
 
 ALL = ["graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
-       "node_update_bwd", "edge_gate_bwd", "segment_sum", "dsilu_mul", "cast"]
+       "node_update_bwd", "edge_gate_bwd", "segment_sum", "segment_sum_pair", "dsilu_mul", "cast"]
 
 
 def install(monkeypatch):

@@ -266,6 +266,20 @@ def test_segment_sum_dst_and_src(prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+def test_segment_sum_pair(prec):
+    N, E, C = 97, 6007, 512
+    plan = _graph(N, E, 3)
+    T = ops.t_dtype(prec)
+    x = rnd(E, C, seed=1).to(T)
+    ref = EM.segment_sum_pair(x, plan.row_ptr, plan.col_ptr, plan.perm_src, N, torch.empty(N, 2 * C, dtype=T), prec)
+    got = ops.segment_sum_pair(x.cuda(), plan.row_ptr.cuda(), plan.col_ptr.cuda(), plan.perm_src.cuda(), N,
+                               torch.empty(N, 2 * C, dtype=T, device="cuda"), prec)
+    assert common.rel_err(got.float(), ref.float()) < (1e-5 if prec == PREC_FP32 else 8e-3)
+    one = ops.segment_sum(x.cuda(), plan.col_ptr.cuda(), plan.perm_src.cuda(), N, torch.empty(N, C, dtype=T, device="cuda"), prec)
+    assert torch.equal(one, got[:, C:])                     # same order of additions as the single-CSR kernel
+
+
+@pytest.mark.parametrize("prec", PRECS)
 def test_elementwise(prec):
     T = ops.t_dtype(prec)
     dy, z = rnd(777, 512, seed=1), rnd(777, 512, seed=2).to(T)
