@@ -37,12 +37,20 @@ def nt(M, Nn, K, mode):
         kw = dict(bias=torch.randn(Nn, device=dev), out_f32=torch.empty(M, Nn, device=dev))
     elif mode == "tout":
         kw = dict(out_t=torch.empty(M, Nn, device=dev, dtype=T))
-    elif mode == "gather_silu":
+    elif mode.startswith("gather_silu"):
         P = torch.randn(N, 2 * Nn, device=dev).to(T)
         dst = torch.sort(torch.randint(0, N, (M,), device=dev))[0].to(torch.int32)
         src = torch.randint(0, N, (M,), device=dev, dtype=torch.int32)
+        if mode == "gather_silu_same":      # both gathers hit one row: L1-resident (isolates the gather path)
+            dst, src = torch.zeros_like(dst), torch.zeros_like(src)
+        elif mode == "gather_silu_local":   # src close to dst (sorted): L1-friendly
+            src = dst.clone()
         kw = dict(bias=torch.randn(Nn, device=dev), gather0=P[:, :Nn], gidx0=dst, gather1=P[:, Nn:], gidx1=src,
                   z_out=torch.empty(M, Nn, device=dev, dtype=T), act=ops.ACT_SILU, out_t=torch.empty(M, Nn, device=dev, dtype=T))
+    elif mode == "resid":
+        kw = dict(resid=torch.randn(M, Nn, device=dev), out_f32=torch.empty(M, Nn, device=dev))
+    elif mode == "bias_tout":
+        kw = dict(bias=torch.randn(Nn, device=dev), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     elif mode == "dsilu":
         kw = dict(act=ops.ACT_MUL_DSILU, z_in=torch.randn(M, Nn, device=dev).to(T), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     ms = timeit(lambda: ops.gemm(prec, A, B, **kw), reps)
@@ -63,6 +71,8 @@ if which in ("all", "nt"):
     nt(E, 256, 256, "dsilu")
     nt(E, 512, 256, "gather_silu")
     nt(E, 256, 512, "f32out")
+    nt(E, 256, 512, "resid")
+    nt(E, 256, 256, "bias_tout")
     nt(E // 8, 256, 256, "tout")
 if which in ("all", "tn"):
     tn(E, 256, 256)
@@ -71,3 +81,5 @@ if which == "one":
     nt(E, 256, 256, "tout")
 if which == "gs":
     nt(E, 512, 256, "gather_silu")
+    nt(E, 512, 256, "gather_silu_local")
+    nt(E, 512, 256, "gather_silu_same")
