@@ -270,8 +270,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = cartnet_b200.CartNet(DIM_IN, DIM_RBF, NUM_LAYERS, precision=args.precision).to(dev)
     broadcast_module(model, 0)
-    sync = FlatGradAllReduce(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sync = FlatGradAllReduce(model.parameters(), direct=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)      # one multi-tensor launch
     model.train()
     from cartnet_b200 import cartnet as CN
     for b in dev_batches:

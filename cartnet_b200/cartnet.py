@@ -215,7 +215,8 @@ class Encoder(nn.Module, _PrecisionMixin):
         else:
             batch.x = self.embedding.weight.repeat(batch.x.shape[0], 1)
         if self.temperature or self.atom_types:
-            batch.x = self.encoder_atom(x)
+            lin = self.encoder_atom[1]                                             # SiLU -> Linear(2D, D) -> SiLU
+            batch.x = CF.linear_silu(F.silu(x), lin.weight, lin.bias, self.prec)
 
         invariant = bool(_cfg_get("invariant", self.invariant))                    # cartnet.py:156
         lin_a, lin_b = self.encoder_edge[0], self.encoder_edge[2]

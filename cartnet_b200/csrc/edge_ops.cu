@@ -559,7 +559,10 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t lds, T* 
     store4<T>(dst + r * ldd + col, *reinterpret_cast<const float4*>(src + r * lds + col));
 }
 
-// feat[e, :] = [ cut(d) exp(-beta_k (exp(-alpha d) - mu_k)^2) (k < R) ; cart_dir (3, unless invariant) ; 0 ... ]
+// feat[e, :] = [ cut(d) exp(-beta_k (exp(-alpha d) - mu_k)^2) (k < R) ; cart_dir (3, unless invariant) ; 1 ; 0 ... ]
+// The first padding column (if ld leaves one) holds 1: the matching column of the zero-padded weight is 0, so the forward
+// is unchanged, while in the backward the bias gradient sum_e dz falls out of the weight-gradient GEMM dz^T feat as that
+// column -- no separate reduction pass over [E, 2D].
 template <typename T, typename R>
 __global__ void edge_features_kernel(const float* __restrict__ cart_dist, const float* __restrict__ cart_dir,
                                      const float* __restrict__ means, const float* __restrict__ betas, int nrbf,
@@ -583,7 +586,7 @@ __global__ void edge_features_kernel(const float* __restrict__ cart_dist, const 
         } else if (!invariant && k < nrbf + 3) {
             v[j] = cart_dir[e * 3 + (k - nrbf)];
         } else {
-            v[j] = 0.f;
+            v[j] = (k == nrbf + (invariant ? 0 : 3)) ? 1.f : 0.f;
         }
     }
     store4<T>(feat + e * ld + col, make_float4(v[0], v[1], v[2], v[3]));

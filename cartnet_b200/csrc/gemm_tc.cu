@@ -344,9 +344,50 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     i1[it] = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
                 }
             }
-            mbar_wait(&bars->tmem_full[acc], acc_phase);
-            tc_fence_after();
+            const bool full = row0 + 32 <= (int64_t)M;
+            bool first = true;
             for (int c = c_begin; c < c_end; c += 32) {
+                const int col = n0 + c + sub_c;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) bias4 = *reinterpret_cast<const float4*>(epi.bias + col);
+                const bool has_g0 = epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr);
+                const bool has_g1 = epi_has<EPI>(EB_GATHER, epi.gather1 != nullptr);
+                const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
+                const bool has_r = epi_has<EPI>(EB_RESID, epi.resid != nullptr);
+                // phase 1: every global read of this 32x32 block is issued up front (8..24 loads in flight per thread) --
+                // before the accumulator is even fetched from TMEM, so that their L2 / HBM round trip overlaps the
+                // tcgen05.ld + shared-memory transpose (and, for a tile's first block, the wait for its MMAs) -- and
+                // before any store, whose possible aliasing would otherwise serialise the round trips.
+                // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
+                // compiler can interleave the 8 independent rows and hide the MUFU / FMA latencies.
+                typename Raw4<T>::type ra[8], rb[8], rz[8];
+                float4 rr[8];
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (full) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
+                        if (has_g0) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                        if (has_g1) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                        if (has_z) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
+                        if (has_r) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int64_t row = row0 + it * 4 + sub_r;
+                        const bool ok = row < M;
+                        if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                        if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                        if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
+                        if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                    }
+                }
+                if (first) {
+                    mbar_wait(&bars->tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    first = false;
+                }
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
 #pragma unroll
@@ -357,30 +398,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                 for (int it = 0; it < 8; ++it) t4[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * NT_STG_PITCH + sub_c);
                 __syncwarp();
-                const int col = n0 + c + sub_c;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) bias4 = *reinterpret_cast<const float4*>(epi.bias + col);
-                const bool has_g0 = epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr);
-                const bool has_g1 = epi_has<EPI>(EB_GATHER, epi.gather1 != nullptr);
-                const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
-                const bool has_r = epi_has<EPI>(EB_RESID, epi.resid != nullptr);
-                // phase 1: every global read of this 32x32 block is issued before any math or store (8..24 loads in
-                // flight per thread), otherwise possible aliasing with the stores would serialise the round trips.
-                // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
-                // compiler can interleave the 8 independent rows and hide the MUFU / FMA latencies.
-                typename Raw4<T>::type ra[8], rb[8], rz[8];
-                float4 rr[8];
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + 32 <= (int64_t)M) {
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        if (has_g0) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                        if (has_g1) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                        if (has_z) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
-                        if (has_r) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
-                    }
-                    float4 ss = zero, sq = zero;
+                float4 ss = zero, sq = zero;
+                if (full) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int64_t row = row0 + it * 4 + sub_r;
@@ -393,18 +412,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
                         }
                     }
-                    if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);
                 } else {
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        const bool ok = row < M;
-                        if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                        if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                        if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
-                        if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
-                    }
-                    float4 ss = zero, sq = zero;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int64_t row = row0 + it * 4 + sub_r;
@@ -419,8 +427,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             }
                         }
                     }
-                    if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
                 }
+                if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
             }
             tc_fence_before();
             __syncwarp();

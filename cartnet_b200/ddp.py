@@ -29,9 +29,15 @@ class FlatGradAllReduce:
     """Keeps every parameter's .grad as a view into one flat buffer so that the gradient exchange is a
     single collective (2,498,438 floats = 9.99 MB for the default CartNet)."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, direct: bool = False):
+        """direct=True additionally lets the hand-written backward kernels store a parameter's gradient straight
+        into its slice of the flat buffer (no AccumulateGrad `+=` launch per parameter). The caller promises what
+        a plain training loop does anyway: zero() before every backward and each parameter used once per
+        backward (no gradient accumulation across micro-batches, no weight sharing)."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        for p in self.params:
+            p._cn_direct_grad = bool(direct)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)

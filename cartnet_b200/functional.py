@@ -66,8 +66,11 @@ class _EdgeEncoderFn(torch.autograd.Function):
         dbb = ops.colsum(dz2, prec)
         dz1 = torch.empty_like(Z1)
         ops.gemm(prec, dz2, _to_t(Wb.t(), prec), act=ACT_MUL_DSILU, z_in=Z1, out_t=dz1)
-        dWa = ops.gemm_tn(prec, dz1, feat)[:, :ctx.dim_edge]            # [2D, dim_edge]
-        dba = ops.colsum(dz1, prec)
+        dWa_full = ops.gemm_tn(prec, dz1, feat)                         # [2D, KF]
+        dWa = dWa_full[:, :ctx.dim_edge]
+        # feat carries a column of ones right after the features when the K padding leaves room (ops.edge_features):
+        # sum_e dz1 is that column of the weight gradient, no reduction pass over [E, 2D]
+        dba = dWa_full[:, ctx.dim_edge].contiguous() if feat.shape[1] > ctx.dim_edge else ops.colsum(dz1, prec)
         return None, None, None, None, dWa, dba, dWb, dbb, None, None, None, None
 
 
@@ -77,6 +80,40 @@ def edge_encoder(cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, upper, invar
     e0 = _EdgeEncoderFn.apply(cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, float(upper), bool(invariant),
                               prec, holder)
     return e0, holder["e_t"]
+
+
+class _LinearSiluFn(torch.autograd.Function):
+    """y = SiLU(x W^T + b) for the node branch of the encoder (/root/reference/models/cartnet.py:125-127,154):
+    [N, 2D] x [D, 2D]^T on the library's GEMMs with the bias + SiLU epilogue and a hand-written backward, instead of
+    three eager cuBLAS SIMT sgemms. Node-side and tiny, so the bf16 mode runs it on the tf32 tensor-core path: no
+    additional bf16 rounding enters the parity budget."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, prec):
+        gp = PREC_TF32 if prec == PREC_BF16 else prec
+        M, N = int(x.shape[0]), int(W.shape[0])
+        x_t = ops.cast(x.detach().contiguous(), gp)
+        Z = torch.empty(M, N, dtype=t_dtype(gp), device=x.device)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        ops.gemm(gp, x_t, _to_t(W, gp), bias=b.detach(), z_out=Z, act=ACT_SILU, out_f32=y)
+        ctx.save_for_backward(x_t, Z, W)
+        ctx.gp = gp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_t, Z, W = ctx.saved_tensors
+        gp = ctx.gp
+        dz = ops.dsilu_mul(dy.contiguous(), Z, gp)                      # [M, N]
+        dW = ops.gemm_tn(gp, dz, x_t)                                   # [N, K]
+        db = ops.colsum(dz, gp)
+        dx = torch.empty(x_t.shape[0], x_t.shape[1], dtype=torch.float32, device=dy.device)
+        ops.gemm(gp, dz, _to_t(W.t(), gp), out_f32=dx)
+        return dx, dW, db, None
+
+
+def linear_silu(x, W, b, prec):
+    return _LinearSiluFn.apply(x, W, b, prec)
 
 
 class _LayerFn(torch.autograd.Function):
@@ -274,6 +311,7 @@ class _NativeLayerFn(torch.autograd.Function):
         cfg["holder"]["e_t"] = e_out_t if shadow else e_out
         ctx.set_materialize_grads(False)     # an unused edge_attr output arrives as None in backward, not as zeros
         ctx.L = L
+        ctx.params = tuple(params.values())      # the Parameters themselves: backward may write straight into their .grad
         ctx.keep = (x, e, x_t, e_t, tbuf, fbuf, dist, plan, cfg["rm1"], cfg["rv1"], cfg["rm2"], cfg["rv2"]) + tuple(
             v.detach() for v in params.values())
         ctx.dims = (N, E, D, prec)
@@ -299,6 +337,16 @@ class _NativeLayerFn(torch.autograd.Function):
         gbuf = torch.empty(8 * D * D + 8 * D, dtype=torch.float32, device=dev)
         (dG1, dA1, dG2, dA2, dbg1, dba1, dbg2, dba2, dw1, db1n, dw2, db2n) = _carve(gbuf, [
             (D, 3 * D), (D, 3 * D), (D, D), (D, D), (D,), (D,), (D,), (D,), (D,), (D,), (D,), (D,)])
+        # Parameters whose owner promised that .grad is (re)written once per backward (ddp.FlatGradAllReduce(direct=True)):
+        # the kernels store the gradient straight into .grad and autograd gets None -- no AccumulateGrad `+=` launch each
+        grads = [dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n]
+        direct = [False] * len(grads)
+        for i, prm in enumerate(ctx.params):
+            tgt = prm.grad if getattr(prm, "_cn_direct_grad", False) else None
+            if (tgt is not None and tgt.is_contiguous() and tgt.dtype == torch.float32 and tgt.device == dev
+                    and tgt.shape == grads[i].shape):
+                grads[i], direct[i] = tgt, True
+        (dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n) = grads
         nbytes = int(lib.cartnet_layer_splitk_bytes(prec, D, N, E))
         ws = ops._workspace(dev, nbytes)
         part = ops._partial(dev, int(lib.cartnet_colstats_workspace(2 * D)))
@@ -310,7 +358,8 @@ class _NativeLayerFn(torch.autograd.Function):
         L.splitk_bytes = ws.numel() * 4
         _lib.check(lib.cartnet_layer_bwd(C.byref(L), ops._stream()), "layer_bwd")
         ctx.keep = None
-        return dx_in, de_in, dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n, None
+        ctx.params = None
+        return (dx_in, de_in) + tuple(None if d else g for g, d in zip(grads, direct)) + (None,)
 
 
 def cartnet_layer_native(x, e, params, cfg):

@@ -102,7 +102,9 @@ int cartnet_graph_csr(const int32_t* keys, int64_t num_edges, int32_t num_nodes,
 /* ---------------------------------------------------------------------------------------
  * Edge featuriser -- replaces models/utils.py:56-61,87-91 and the cat at cartnet.py:159.
  * feat[E, ld] (T): cols 0..num_rbf-1 = cut(d)*exp(-beta_k (exp(-alpha d) - mu_k)^2), then (unless
- * invariant) 3 cols cart_dir, remaining cols up to ld zero.
+ * invariant) 3 cols cart_dir, then (if ld leaves room) ONE column of ones -- the matching column of the
+ * zero-padded weight is 0, so it only serves the backward: d(bias) = that column of dz^T feat -- and the
+ * remaining cols up to ld zero.
  * ------------------------------------------------------------------------------------- */
 int cartnet_edge_features(const float* cart_dist, const float* cart_dir, const float* means,
                           const float* betas, int32_t num_rbf, float cutoff_upper, int32_t invariant,

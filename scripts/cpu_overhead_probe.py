@@ -15,8 +15,8 @@ hb = bench.make_host_batch(B, 2, dev)
 db = bench.shallow(hb.clone()).to(dev)
 torch.manual_seed(0)
 model = cartnet_b200.CartNet(256, 64, 4, precision="bf16").to(dev).train()
-sync = FlatGradAllReduce(model.parameters())
-opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+sync = FlatGradAllReduce(model.parameters(), direct=True)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
 CN.get_plan(db)
 
 def step():

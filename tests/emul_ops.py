@@ -83,7 +83,10 @@ def edge_features(cart_dist, cart_dir, means, betas, cutoff_upper, invariant, ld
     rbf = cut * torch.exp(-betas * (torch.exp(alpha * (-d)) - means) ** 2)
     parts = [rbf] if invariant else [rbf, cart_dir]
     feat = torch.cat(parts, dim=-1)
-    feat = F.pad(feat, (0, ld - feat.shape[1]))
+    used = feat.shape[1]
+    feat = F.pad(feat, (0, ld - used))
+    if ld > used:
+        feat[:, used] = 1.0          # ones column: the bias gradient rides in the weight-gradient GEMM
     return feat.to(t_dtype(prec))
 
 

@@ -257,3 +257,25 @@ def test_tf32_mode_eval_within_2e3_on_every_golden_case(golden_model, name):
     with torch.no_grad():
         pred, _ = model(batch0.clone())
     assert common.rel_err(pred, torch.from_numpy(golden_model[name + "/pred_eval"])) < 2e-3
+
+
+def test_direct_gradient_writes_are_bit_identical():
+    """ddp.FlatGradAllReduce(direct=True): the layer backward stores weight gradients straight into the flat
+    gradient buffer (no AccumulateGrad launch per parameter); values must equal the autograd-accumulated ones."""
+    from cartnet_b200.ddp import FlatGradAllReduce
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
+    batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
+    flats = []
+    for direct in (False, True):
+        torch.manual_seed(0)
+        model = cartnet_b200.CartNet(256, 64, 4, radius=lrad, precision="bf16", **kw)
+        model.load_state_dict(fixtures.make_state_dict(model.state_dict(), seed))
+        model.cuda().train()
+        sync = FlatGradAllReduce(model.parameters(), direct=direct)
+        for _ in range(2):                       # second pass: stale values from the first must be overwritten
+            sync.zero()
+            pred, true = model(batch0.clone())
+            torch.nn.functional.l1_loss(pred, true).backward()
+        flats.append(sync.flat.clone())
+        assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())
+    assert torch.equal(flats[0], flats[1])

@@ -36,10 +36,14 @@ def test_edge_features_golden(golden_feat):
     d = torch.from_numpy(golden_feat["dist"]).cuda()
     means, betas = torch.from_numpy(golden_feat["means"]).cuda(), torch.from_numpy(golden_feat["betas"]).cuda()
     cdir = torch.nn.functional.normalize(rnd(d.numel(), 3), dim=-1).cuda()
-    f = ops.edge_features(d, cdir, means, betas, 5.0, False, 68, PREC_FP32)
+    f = ops.edge_features(d, cdir, means, betas, 5.0, False, 72, PREC_FP32)
     ref = torch.from_numpy(golden_feat["rbf"])
     assert float((f[:, :64].cpu() - ref).abs().max()) < 2e-6          # reference RBF values, absolute (values in [0,1])
-    assert torch.equal(f[:, 64:67], cdir) and float(f[:, 67:].abs().max()) == 0.0
+    assert torch.equal(f[:, 64:67], cdir)
+    # K padding: one column of ones (bias gradient rides in the weight-gradient GEMM), then zeros
+    assert torch.equal(f[:, 67], torch.ones_like(d)) and float(f[:, 68:].abs().max()) == 0.0
+    assert torch.equal(f.cpu(), EM.edge_features(d.cpu(), cdir.cpu(), means.cpu(), betas.cpu(), 5.0, False, 72, PREC_FP32)[:, :72]) or \
+        float((f.cpu() - EM.edge_features(d.cpu(), cdir.cpu(), means.cpu(), betas.cpu(), 5.0, False, 72, PREC_FP32)).abs().max()) < 2e-6
     f2 = ops.edge_features(d, None, means, betas, 5.0, True, 64, PREC_FP32)
     assert torch.equal(f2, f[:, :64])
 
