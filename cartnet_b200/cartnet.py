@@ -206,18 +206,9 @@ class Encoder(nn.Module, _PrecisionMixin):
         self.rbf = ExpNormalSmearingParams(radius, dim_rbf)
 
     def forward(self, batch):
-        if self.temperature and self.atom_types:                                   # cartnet.py:144-151
-            x = self.embedding(batch.x) + _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
-        elif not self.temperature and self.atom_types:
-            x = self.embedding(batch.x) + self.bias
-        elif self.temperature and not self.atom_types:
-            x = _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
-        else:
-            batch.x = self.embedding.weight.repeat(batch.x.shape[0], 1)
-        if self.temperature or self.atom_types:
-            lin = self.encoder_atom[1]                                             # SiLU -> Linear(2D, D) -> SiLU
-            batch.x = CF.linear_silu(F.silu(x), lin.weight, lin.bias, self.prec)
-
+        # Edge branch first (cartnet.py:156-159): its three launches are ~1 ms of device work, issued before the ~30 small
+        # node-side launches below so that the GPU is busy while the host walks through those (the two branches are
+        # independent; after a host sync -- e.g. the loss read of the previous step -- the device would otherwise idle).
         invariant = bool(_cfg_get("invariant", self.invariant))                    # cartnet.py:156
         lin_a, lin_b = self.encoder_edge[0], self.encoder_edge[2]
         if int(lin_a.weight.shape[1]) != self.rbf.num_rbf + (0 if invariant else 3):
@@ -235,6 +226,18 @@ class Encoder(nn.Module, _PrecisionMixin):
             batch.edge_attr = e0[inv]
         else:
             batch.edge_attr = _tag(e0, e0_t, self.prec)
+
+        if self.temperature and self.atom_types:                                   # cartnet.py:144-151
+            x = self.embedding(batch.x) + _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
+        elif not self.temperature and self.atom_types:
+            x = self.embedding(batch.x) + self.bias
+        elif self.temperature and not self.atom_types:
+            x = _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
+        else:
+            batch.x = self.embedding.weight.repeat(batch.x.shape[0], 1)
+        if self.temperature or self.atom_types:
+            lin = self.encoder_atom[1]                                             # SiLU -> Linear(2D, D) -> SiLU
+            batch.x = CF.linear_silu(F.silu(x), lin.weight, lin.bias, self.prec)
         return batch
 
 
