@@ -10,7 +10,7 @@ ADP shape) on N B200s of one node, with the reference CPU path timed beside it.
 Workload (config.workload): BASELINE configs[1] -- "CartNet ADP training step, batch 64 crystals, 1xB200":
 64 synthetic ADP-shaped crystals per GPU (lognormal sizes, mean ~194 atoms, 9.5 A^3/atom, radius 5 A),
 random-init CartNet(256, 64, 4 layers, Cholesky head), one step = forward + L1 loss + backward +
-gradient all-reduce (N > 1) + Adam. Weak scaling: every rank gets its own 64-crystal batches.
+gradient all-reduce (N > 1) + Adam. Weak scaling: the global batch is 64 x N crystals, sharded as whole crystals per rank balanced by edge count.
 Graphs are built by the product's own neighbour-list kernel before the timed region (the reference builds
 graphs offline too).
 """
@@ -44,9 +44,9 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------- workload
-def host_structures(batch: int, seed: int):
+def host_structures(structs, seed: int):
+    """Collated HOST tensors of a list of synthetic crystals (cartnet_b200.synthetic.make_structures)."""
     from cartnet_b200 import synthetic
-    structs = synthetic.make_structures("adp", batch, seed)
     rng = np.random.default_rng(seed + 7919)
     z = np.concatenate([s["z"] for s in structs])
     mask = z != 1
@@ -56,16 +56,31 @@ def host_structures(batch: int, seed: int):
         natoms=torch.tensor([len(s["z"]) for s in structs], dtype=torch.int64),
         temperature=torch.tensor([s["temperature"] for s in structs], dtype=torch.float32),
         non_H_mask=torch.from_numpy(mask), y=torch.from_numpy(synthetic.adp_targets(int(mask.sum()), rng)))
-    out["batch"] = torch.repeat_interleave(torch.arange(batch), out["natoms"])
+    out["batch"] = torch.repeat_interleave(torch.arange(len(structs)), out["natoms"])
     return out
 
 
-def make_host_batch(batch: int, seed: int, device):
+def rank_structures(batch: int, seed: int, rank: int, world: int, device):
+    """This rank's crystals of the step's GLOBAL batch (batch * world crystals from one seed). SURVEY.md 8(e): whole
+    crystals per rank, balanced by EDGE count (cartnet_b200.ddp.shard_by_edges, LPT) -- the layer cost is linear in
+    edges, and the step time of a data-parallel job is the slowest rank's. world == 1: all crystals, in order."""
+    from cartnet_b200 import build_graph, synthetic
+    from cartnet_b200.ddp import shard_by_edges
+    structs = synthetic.make_structures("adp", batch * world, seed)
+    if world == 1:
+        return structs
+    h = host_structures(structs, seed)
+    gr = build_graph(h["pos"].to(device), h["cell"].to(device), h["natoms"].to(device), 5.0)
+    counts = torch.bincount(h["batch"].to(device)[gr["edge_index"][1]], minlength=len(structs)).cpu().tolist()
+    return [structs[i] for i in shard_by_edges(counts, world)[rank]]
+
+
+def make_host_batch(structs, seed: int, device):
     """Synthetic crystals + graph built by the GPU neighbour-list kernel, returned as a pinned HOST batch
     (what a DataLoader with pin_memory=True hands to train.py:169)."""
     from cartnet_b200 import build_graph
     from cartnet_b200.batch import CrystalBatch
-    h = host_structures(batch, seed)
+    h = host_structures(structs, seed)
     gr = build_graph(h["pos"].to(device), h["cell"].to(device), h["natoms"].to(device), 5.0)
     h["edge_index"], h["cart_dist"], h["cart_dir"] = gr["edge_index"].cpu(), gr["cart_dist"].cpu(), gr["cart_dir"].cpu()
     # facts the data pipeline knows statically: radius_graph_pbc output is dst-sorted; the non-H atom list is fixed
@@ -263,9 +278,11 @@ def run_ours(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     nb = 2
-    host_batches = [make_host_batch(args.batch, args.seed + 1000 * rank + i, dev) for i in range(nb)]
+    # step i of every rank works on its shard of global batch i (args.batch * world crystals, seed + i)
+    host_batches = [make_host_batch(rank_structures(args.batch, args.seed + i, rank, world, dev), args.seed + 1000 * rank + i, dev)
+                    for i in range(nb)]
     dev_batches = [shallow(hb).to(dev) for hb in [b.clone() for b in host_batches]]
-    graphs_step = args.batch
+    graphs_step = args.batch                     # per rank on average: the global batch has args.batch * world crystals
     edges_step = float(np.mean([b.num_edges for b in host_batches]))
     nodes_step = float(np.mean([b.num_nodes for b in host_batches]))
 
@@ -393,7 +410,7 @@ def run_ours(args):
         "config": {"workload": "CartNet ADP training step (fwd+bwd+Adam), batch %d crystals per GPU" % args.batch,
                    "crystals_per_gpu": args.batch, "atoms_per_gpu": nodes_step, "edges_per_gpu": edges_step, "radius": 5.0,
                    "dim_in": DIM_IN, "dim_rbf": DIM_RBF, "num_layers": NUM_LAYERS, "precision": args.precision,
-                   "parallelism": "crystals sharded per GPU, one NCCL all-reduce of the flat gradient per step" if world > 1 else "single GPU",
+                   "parallelism": "global batch of %d crystals sharded as whole crystals per GPU, balanced by edge count (LPT); one NCCL all-reduce of the flat gradient per step" % (args.batch * world) if world > 1 else "single GPU",
                    "l2": "per-step working set ~%.1f GB of activations >> 126 MB L2; %d distinct batches cycled" % (act_gb, nb)},
         "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,

@@ -14,7 +14,7 @@ from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 STEPS = 4
-hb = bench.make_host_batch(B, 2, dev)
+hb = bench.make_host_batch(bench.rank_structures(B, 2, 0, 1, dev), 2, dev)
 db = bench.shallow(hb.clone()).to(dev)
 torch.manual_seed(0)
 model = cartnet_b200.CartNet(256, 64, 4, precision="bf16").to(dev).train()
