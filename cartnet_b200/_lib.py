@@ -87,6 +87,9 @@ SIGNATURES = {
     "cartnet_layer_pack_weights": (i32, [C.POINTER(LayerDesc), vp]),
     "cartnet_layer_fwd": (i32, [C.POINTER(LayerDesc), vp]),
     "cartnet_layer_bwd": (i32, [C.POINTER(LayerDesc), vp]),
+    "cartnet_cholesky_head_workspace": (i64, [i32, i32]),
+    "cartnet_cholesky_head_fwd": (i32, [vp, i64, vp, vp, i32, i32, vp, vp, vp]),
+    "cartnet_cholesky_head_bwd": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, i64, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -307,26 +307,22 @@ class CartNet_layer(nn.Module, _PrecisionMixin):
         return batch
 
 
-class Cholesky_head(nn.Module):
-    """Plain PyTorch, as in /root/reference/models/cartnet.py:276-305 (node-side, negligible)."""
+class Cholesky_head(nn.Module, _PrecisionMixin):
+    """Mirror of /root/reference/models/cartnet.py:276-305. The first Linear + SiLU runs on the library GEMM, the rest
+    (Linear(D/2, 6), softplus diagonal, upper-triangular L, U = L^T L) is one fused kernel per direction."""
 
-    def __init__(self, dim_in: int):
+    def __init__(self, dim_in: int, precision: str | None = None):
         super().__init__()
+        self.precision = precision or default_precision()
         self.MLP = nn.Sequential(nn.Linear(dim_in, dim_in // 2), nn.SiLU(inplace=True), nn.Linear(dim_in // 2, 6))
 
     def forward(self, batch):
         idx = getattr(batch, "non_H_index", None)        # optional precomputed nonzero(non_H_mask) from the data pipeline
         if idx is None:
             idx = _mask_index(batch.non_H_mask)
-        pred = self.MLP(batch.x.index_select(0, idx))                                # == batch.x[batch.non_H_mask]
-        d = F.softplus(pred[:, :3])
-        z = torch.zeros_like(d[:, 0])
-        # upper-triangular L with softplus diagonal (cartnet.py:296-301), assembled with stack instead of advanced
-        # indexing: index tensors built from Python lists would be copied host->device (a sync) on every call
-        L = torch.stack([torch.stack([d[:, 0], pred[:, 3], pred[:, 4]], dim=-1),
-                         torch.stack([z, d[:, 1], pred[:, 5]], dim=-1),
-                         torch.stack([z, z, d[:, 2]], dim=-1)], dim=1)
-        return torch.bmm(L.transpose(1, 2), L), batch.y
+        x = batch.x.index_select(0, idx)                                             # == batch.x[batch.non_H_mask]
+        h = CF.linear_silu(x, self.MLP[0].weight, self.MLP[0].bias, self.prec)
+        return CF.cholesky_tail(h, self.MLP[2].weight, self.MLP[2].bias), batch.y
 
 
 class Scalar_head(nn.Module):
@@ -361,7 +357,7 @@ class CartNet(nn.Module, _PrecisionMixin):
         self.dim_in = dim_in
         self.layers = nn.Sequential(*[CartNet_layer(dim_in=dim_in, use_envelope=use_envelope, radius=radius,
                                                     precision=self.precision) for _ in range(num_layers)])
-        self.head = Cholesky_head(dim_in) if cholesky else Scalar_head(dim_in)
+        self.head = Cholesky_head(dim_in, precision=self.precision) if cholesky else Scalar_head(dim_in)
 
     def forward(self, batch):
         batch = self.encoder(batch)

@@ -16,6 +16,7 @@
 //   * each CTA owns a 256 x Nblk output block (two M=128 accumulators = up to 512 TMEM columns) and a
 //     contiguous K range; partial blocks go to a workspace and are summed in a fixed order (deterministic).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -614,8 +615,9 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     CN_CHECK_ARG(d.K % TR::KB == 0, "tcgen05 gemm: K=%d must be a multiple of %d", d.K, TR::KB);
     // resident weight slice: largest BN with BN*K*esize <= 128 KB that divides N
     int BN = 0;
+    static const int bn_cap = getenv("CARTNET_NT_BN_CAP") ? atoi(getenv("CARTNET_NT_BN_CAP")) : 256;   // tuning knob (experiments)
     for (int cand : {256, 128, 64, 32})
-        if ((int64_t)cand * d.K * esize <= 131072 && d.N % cand == 0) { BN = cand; break; }
+        if (cand <= bn_cap && (int64_t)cand * d.K * esize <= 131072 && d.N % cand == 0) { BN = cand; break; }
     CN_CHECK_ARG(BN > 0, "tcgen05 gemm: no resident tile for N=%d K=%d", d.N, d.K);
     const int n_tiles = d.N / BN, m_tiles = ceil_div(d.M, 128);
     CN_CHECK_ARG(n_tiles <= kNumSMs, "tcgen05 gemm: too many N tiles (%d)", n_tiles);

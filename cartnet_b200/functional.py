@@ -105,7 +105,10 @@ class _LinearSiluFn(torch.autograd.Function):
         x_t, Z, W = ctx.saved_tensors
         gp = ctx.gp
         dz = ops.dsilu_mul(dy.contiguous(), Z, gp)                      # [M, N]
-        dW = ops.gemm_tn(gp, dz, x_t)                                   # [N, K]
+        if dz.shape[1] % 256 != 0 and x_t.shape[1] % 256 == 0:
+            dW = ops.gemm_tn(gp, x_t, dz).t()                           # [K, N]^T: the tcgen05 TN kernel owns 256-row blocks
+        else:
+            dW = ops.gemm_tn(gp, dz, x_t)                               # [N, K]
         db = ops.colsum(dz, gp)
         dx = torch.empty(x_t.shape[0], x_t.shape[1], dtype=torch.float32, device=dy.device)
         ops.gemm(gp, dz, _to_t(W.t(), gp), out_f32=dx)
@@ -114,6 +117,28 @@ class _LinearSiluFn(torch.autograd.Function):
 
 def linear_silu(x, W, b, prec):
     return _LinearSiluFn.apply(x, W, b, prec)
+
+
+class _CholeskyTailFn(torch.autograd.Function):
+    """(h [n, Dh], W1 [6, Dh], b1 [6]) -> U [n,3,3] = L^T L with L upper triangular, softplus diagonal
+    (/root/reference/models/cartnet.py:293-303): one launch forward, two backward."""
+
+    @staticmethod
+    def forward(ctx, h, W1, b1):
+        h = h.detach().contiguous()
+        U, p6 = ops.cholesky_head_fwd(h, W1.detach().contiguous(), b1.detach().contiguous())
+        ctx.save_for_backward(h, p6, W1)
+        return U
+
+    @staticmethod
+    def backward(ctx, dU):
+        h, p6, W1 = ctx.saved_tensors
+        dh, dW1, db1 = ops.cholesky_head_bwd(dU.contiguous(), h, p6, W1.detach().contiguous())
+        return dh, dW1, db1
+
+
+def cholesky_tail(h, W1, b1):
+    return _CholeskyTailFn.apply(h, W1, b1)
 
 
 class _LayerFn(torch.autograd.Function):

@@ -462,3 +462,29 @@ def cast(x, prec: int) -> torch.Tensor:
     y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=x.device)
     _lib.check(lib.cartnet_cast_rows(_p(x), _ld2(x), _p(y), Cc, rows, Cc, prec, _stream()), "cast_rows")
     return y
+
+
+# ----------------------------------------------------------------------------- Cholesky head tail
+def cholesky_head_fwd(h, W1, b1):
+    """h [n, Dh] fp32 -> (U [n,3,3] = L^T L, p6 [n,6] = h W1^T + b1) in one launch (cartnet.py:293-303)."""
+    lib = _lib.load()
+    _req(h, torch.float32, "h"); _req(W1, torch.float32, "W1"); _req(b1, torch.float32, "b1", rowmajor=False)
+    n, Dh = int(h.shape[0]), int(h.shape[1])
+    p6 = torch.empty(n, 6, dtype=torch.float32, device=h.device)
+    U = torch.empty(n, 3, 3, dtype=torch.float32, device=h.device)
+    _lib.check(lib.cartnet_cholesky_head_fwd(_p(h), _ld2(h), _p(W1), _p(b1), n, Dh, _p(p6), _p(U), _stream()), "cholesky_head_fwd")
+    return U, p6
+
+
+def cholesky_head_bwd(dU, h, p6, W1):
+    """-> (dh [n, Dh], dW1 [6, Dh], db1 [6]); deterministic reduction over atoms."""
+    lib = _lib.load()
+    _req(dU, torch.float32, "dU", rowmajor=False); _req(h, torch.float32, "h"); _req(p6, torch.float32, "p6")
+    n, Dh = int(h.shape[0]), int(h.shape[1])
+    dh = torch.empty(n, Dh, dtype=torch.float32, device=h.device)
+    dW1 = torch.empty(6, Dh, dtype=torch.float32, device=h.device)
+    db1 = torch.empty(6, dtype=torch.float32, device=h.device)
+    part = _workspace(h.device, int(lib.cartnet_cholesky_head_workspace(n, Dh)))
+    _lib.check(lib.cartnet_cholesky_head_bwd(_p(dU), _p(h), _ld2(h), _p(p6), _p(W1), n, Dh, _p(dh), Dh, _p(dW1), _p(db1),
+                                             _p(part), _stream()), "cholesky_head_bwd")
+    return dh, dW1, db1

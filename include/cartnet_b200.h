@@ -326,6 +326,22 @@ int cartnet_layer_pack_weights(const cartnet_layer_t* L /* host */, cartnet_stre
 int cartnet_layer_fwd(const cartnet_layer_t* L /* host */, cartnet_stream_t stream);
 int cartnet_layer_bwd(const cartnet_layer_t* L /* host */, cartnet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Cholesky head tail -- replaces models/cartnet.py:293-305 after the head's first Linear + SiLU
+ * (SURVEY.md 8(f)3). h [n, Dh] fp32 (row pitch ldh) is the SiLU output for the n non-H atoms.
+ *   fwd: p6 [n,6] = h W1^T + b1 (saved for backward);  d = softplus(p6[:, 0:3]);
+ *        L = [[d0,p3,p4],[0,d1,p5],[0,0,d2]] (upper triangular, cartnet.py:296-301);  U [n,3,3] = L^T L.
+ *   bwd: dU [n,3,3] (any, not necessarily symmetric) -> dh [n, Dh] (row pitch lddh), dW1 [6, Dh], db1 [6].
+ *        The reduction over atoms is fixed-order (deterministic); partial >= cartnet_cholesky_head_workspace bytes.
+ * Dh % 4 == 0, Dh <= 512. fp32 arithmetic in every precision mode (node-side, negligible cost).
+ * ------------------------------------------------------------------------------------- */
+int64_t cartnet_cholesky_head_workspace(int32_t n, int32_t Dh);
+int cartnet_cholesky_head_fwd(const float* h, int64_t ldh, const float* W1, const float* b1, int32_t n, int32_t Dh,
+                              float* p6, float* U, cartnet_stream_t stream);
+int cartnet_cholesky_head_bwd(const float* dU, const float* h, int64_t ldh, const float* p6, const float* W1, int32_t n,
+                              int32_t Dh, float* dh, int64_t lddh, float* dW1, float* db1, float* partial,
+                              cartnet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -223,7 +223,31 @@ def cast(x, prec):
     return _shadow(x, prec)
 
 
-ALL = ["graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
+def _chol_L(p6):
+    d = F.softplus(p6[:, :3])
+    z = torch.zeros_like(d[:, 0])
+    return torch.stack([torch.stack([d[:, 0], p6[:, 3], p6[:, 4]], dim=-1),
+                        torch.stack([z, d[:, 1], p6[:, 5]], dim=-1),
+                        torch.stack([z, z, d[:, 2]], dim=-1)], dim=1)
+
+
+def cholesky_head_fwd(h, W1, b1):
+    p6 = (_f(h) @ _f(W1).t() + _f(b1)).float()
+    L = _chol_L(_f(p6))
+    return torch.bmm(L.transpose(1, 2), L).float(), p6
+
+
+def cholesky_head_bwd(dU, h, p6, W1):
+    p = _f(p6)
+    L = _chol_L(p)
+    G = _f(dU)
+    dL = torch.bmm(L, G + G.transpose(1, 2))
+    dp = torch.stack([dL[:, 0, 0] * torch.sigmoid(p[:, 0]), dL[:, 1, 1] * torch.sigmoid(p[:, 1]), dL[:, 2, 2] * torch.sigmoid(p[:, 2]),
+                      dL[:, 0, 1], dL[:, 0, 2], dL[:, 1, 2]], dim=-1)
+    return (dp @ _f(W1)).float(), (dp.t() @ _f(h)).float(), dp.sum(0).float()
+
+
+ALL = ["cholesky_head_fwd", "cholesky_head_bwd", "graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
        "node_update_bwd", "edge_gate_bwd", "segment_sum", "segment_sum_pair", "dsilu_mul", "cast"]
 
 

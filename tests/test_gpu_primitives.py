@@ -291,3 +291,52 @@ def test_elementwise(prec):
     assert common.rel_err(got.float(), ref.float()) < (2e-6 if prec == PREC_FP32 else 8e-3)
     ref, got = both("cast", (dy, prec))
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_linear_silu_matches_torch(precision):
+    """Node branch of the encoder (cartnet.py:125-127): y = SiLU(x W^T + b) on the library GEMMs with the hand-written
+    backward, against eager torch fp32. bf16 mode runs this node-side GEMM on the tf32 path."""
+    from cartnet_b200 import functional as CF
+    prec = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": ops.PREC_BF16}[precision]
+    M, K, N = 777, 512, 256
+    x = rnd(M, K, seed=3).cuda().requires_grad_(True)
+    W = rnd(N, K, seed=4, scale=K ** -0.5).cuda().requires_grad_(True)
+    b = rnd(N, seed=5, scale=0.1).cuda().requires_grad_(True)
+    dy = rnd(M, N, seed=6).cuda()
+    y = CF.linear_silu(x, W, b, prec)
+    y.backward(dy)
+    got = [y.detach(), x.grad.clone(), W.grad.clone(), b.grad.clone()]
+    x.grad = W.grad = b.grad = None
+    yr = torch.nn.functional.silu(torch.nn.functional.linear(x, W, b))
+    yr.backward(dy)
+    tol = 2e-6 if precision == "fp32" else 2e-3
+    for g, r in zip(got, [yr.detach(), x.grad, W.grad, b.grad]):
+        assert common.rel_err(g, r) < tol
+
+
+@pytest.mark.parametrize("n,Dh", [(1, 128), (777, 128), (5000, 128), (33, 64), (40, 256), (0, 128)])
+def test_cholesky_head_tail(n, Dh):
+    """cartnet_cholesky_head_fwd / _bwd (cartnet.py:293-303: Linear(Dh, 6), softplus diagonal, upper-triangular L,
+    U = L^T L) against the plain-torch specification, and against autograd through that specification."""
+    h, W1, b1 = rnd(n, Dh, seed=1), rnd(6, Dh, seed=2, scale=Dh ** -0.5), rnd(6, seed=3)
+    b1[0] = 25.0 if n else b1[0]                           # exercises the softplus threshold branch
+    dU = rnd(n, 3, 3, seed=4)
+    U_ref, p_ref = EM.cholesky_head_fwd(h, W1, b1)
+    U, p6 = ops.cholesky_head_fwd(h.cuda(), W1.cuda(), b1.cuda())
+    if n == 0:
+        assert U.shape == (0, 3, 3)
+        dh, dW1, db1 = ops.cholesky_head_bwd(dU.cuda(), h.cuda(), p6, W1.cuda())
+        assert float(dW1.abs().max()) == 0.0 and float(db1.abs().max()) == 0.0
+        return
+    assert common.rel_err(p6, p_ref) < 2e-6 and common.rel_err(U, U_ref) < 5e-6
+    assert torch.equal(U, U.transpose(1, 2))               # exactly symmetric, like L^T L in the reference
+    hh, ww, bb = (t.clone().double().requires_grad_(True) for t in (h, W1, b1))
+    pa = hh @ ww.t() + bb
+    La = EM._chol_L(pa)
+    (torch.bmm(La.transpose(1, 2), La) * dU.double()).sum().backward()
+    dh, dW1, db1 = ops.cholesky_head_bwd(dU.cuda(), h.cuda(), p6, W1.cuda())
+    for got, ref in ((dh, hh.grad), (dW1, ww.grad), (db1, bb.grad)):
+        assert common.rel_err(got, ref) < 1e-5
+    dh2, dW2, db2 = ops.cholesky_head_bwd(dU.cuda(), h.cuda(), p6, W1.cuda())
+    assert torch.equal(dW1, dW2) and torch.equal(db1, db2) and torch.equal(dh, dh2)     # deterministic reduction
