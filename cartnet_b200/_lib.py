@@ -81,7 +81,7 @@ SIGNATURES = {
     "cartnet_edge_gate_bwd_apply": (i32, [vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, i32, vp]),
     "cartnet_segment_sum": (i32, [vp, i64, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "cartnet_segment_sum_pair": (i32, [vp, i64, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
-    "cartnet_dsilu_mul": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]),
+    "cartnet_dsilu_mul": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),
     "cartnet_cast_rows": (i32, [vp, i64, vp, i64, i64, i32, i32, vp]),
     "cartnet_layer_splitk_bytes": (i64, [i32, i32, i32, i64]),
     "cartnet_layer_pack_weights": (i32, [C.POINTER(LayerDesc), vp]),

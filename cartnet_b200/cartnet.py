@@ -258,6 +258,7 @@ class CartNet_layer(nn.Module, _PrecisionMixin):
         self.norm2 = nn.BatchNorm1d(dim_in)
         self.use_envelope = use_envelope
         self.radius = float(_cfg_get("radius", 5.0 if radius is None else radius))   # cartnet.py:201
+        self.emit_edge_operand = True        # CartNet clears it on its last layer (nothing consumes that operand copy)
 
     def _packed(self):
         W1n, W1e = _PackW1.apply(self.MLP_gate[0].weight, self.MLP_aggr[0].weight)     # [D, 3D], columns [x_i | x_j | e]
@@ -284,7 +285,7 @@ class CartNet_layer(nn.Module, _PrecisionMixin):
             e, dist, e_t = e[plan.perm_dst], dist[plan.perm_dst], None
         holder = {}
         cfg = dict(prec=prec, plan=plan, dist=dist.contiguous(), x_t=x_t, e_t=e_t, training=training,
-                   radius=self.radius, use_envelope=self.use_envelope, holder=holder,
+                   radius=self.radius, use_envelope=self.use_envelope, holder=holder, want_e_operand=self.emit_edge_operand,
                    rm1=self.norm.running_mean, rv1=self.norm.running_var, momentum1=self._momentum(self.norm),
                    rm2=self.norm2.running_mean, rv2=self.norm2.running_var, momentum2=self._momentum(self.norm2))
         if CF.USE_NATIVE_LAYER:      # one C-ABI call per direction (csrc/layer.cu)
@@ -325,16 +326,48 @@ class Cholesky_head(nn.Module, _PrecisionMixin):
         return CF.cholesky_tail(h, self.MLP[2].weight, self.MLP[2].bias), batch.y
 
 
-class Scalar_head(nn.Module):
-    """Plain PyTorch, as in /root/reference/models/cartnet.py:307-327 (mean pooling by index_add)."""
+class _SegmentMean(torch.autograd.Function):
+    """Per-crystal mean of node rows for a SORTED batch vector: a deterministic segmented sum over each crystal's
+    contiguous node range (C-ABI cartnet_segment_sum) instead of torch_scatter's atomic scatter (cartnet.py:326)."""
 
-    def __init__(self, dim_in: int):
+    @staticmethod
+    def forward(ctx, rows, batch_vec, natoms):
+        num_graphs = int(natoms.numel())
+        nat = natoms.to(rows.device)
+        ptr = torch.zeros(num_graphs + 1, dtype=torch.int32, device=rows.device)
+        ptr[1:] = torch.cumsum(nat, 0).to(torch.int32)
+        inv = 1.0 / nat.clamp(min=1).to(torch.float32).unsqueeze(-1)
+        out = torch.empty(num_graphs, rows.shape[1], dtype=torch.float32, device=rows.device)
+        ops.segment_sum(rows.detach().contiguous(), ptr, None, num_graphs, out, PREC_FP32)
+        ctx.save_for_backward(batch_vec, inv)
+        return out * inv
+
+    @staticmethod
+    def backward(ctx, grad):
+        batch_vec, inv = ctx.saved_tensors
+        return (grad * inv).index_select(0, batch_vec), None, None
+
+
+class Scalar_head(nn.Module, _PrecisionMixin):
+    """Mirror of /root/reference/models/cartnet.py:307-327. With PyG-style batches (natoms known, nodes grouped by
+    crystal) the first Linear + SiLU runs on the library GEMM and the mean pooling is a deterministic segmented sum
+    taken BEFORE the last Linear (mean_g(W h + b) = W mean_g(h) + b: pooled rows are D/2 wide, the kernel's shape; no
+    device->host read of batch.batch.max() as at cartnet.py:324). Otherwise: eager index_add pooling."""
+
+    def __init__(self, dim_in: int, precision: str | None = None):
         super().__init__()
+        self.precision = precision or default_precision()
         self.MLP = nn.Sequential(nn.Linear(dim_in, dim_in // 2), nn.SiLU(inplace=True), nn.Linear(dim_in // 2, 1))
 
     def forward(self, batch):
         natoms = getattr(batch, "natoms", None)
-        dim_size = int(natoms.numel()) if natoms is not None else int(batch.batch.max().item() + 1)
+        c = self.MLP[0].out_features
+        if natoms is not None and c % 4 == 0 and c // 4 <= 256 and 256 % (c // 4) == 0:
+            h = CF.linear_silu(batch.x, self.MLP[0].weight, self.MLP[0].bias, self.prec)
+            pooled = _SegmentMean.apply(h, batch.batch, natoms)
+            batch.x = F.linear(pooled, self.MLP[2].weight, self.MLP[2].bias).squeeze(-1)
+            return batch.x, batch.y
+        dim_size = int(batch.batch.max().item() + 1)
         h = self.MLP(batch.x)
         tot = torch.zeros(dim_size, 1, dtype=h.dtype, device=h.device).index_add_(0, batch.batch, h)
         cnt = torch.zeros(dim_size, dtype=h.dtype, device=h.device).index_add_(
@@ -357,7 +390,9 @@ class CartNet(nn.Module, _PrecisionMixin):
         self.dim_in = dim_in
         self.layers = nn.Sequential(*[CartNet_layer(dim_in=dim_in, use_envelope=use_envelope, radius=radius,
                                                     precision=self.precision) for _ in range(num_layers)])
-        self.head = Cholesky_head(dim_in, precision=self.precision) if cholesky else Scalar_head(dim_in)
+        if num_layers > 0:
+            self.layers[-1].emit_edge_operand = False
+        self.head = Cholesky_head(dim_in, precision=self.precision) if cholesky else Scalar_head(dim_in, precision=self.precision)
 
     def forward(self, batch):
         batch = self.encoder(batch)

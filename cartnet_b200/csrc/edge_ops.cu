@@ -219,6 +219,25 @@ struct SumF {
     __device__ void load(int64_t r, int col, In& in) const { in = load4<TX>(x + r * ld + col); }
     __device__ void compute(const State&, int64_t, int, const In& a, float4* o) const { o[0] = a; }
 };
+// y = (T)(dy * silu'(z)) written on the fly, column sums of y (a bias gradient) as the reduction
+template <typename T>
+struct DsiluMulF {
+    static constexpr int NV = 1;
+    static constexpr bool F32_PARTIAL = true;
+    using State = NoState;
+    struct In { float4 d, z; };
+    const float* dy; int64_t ld_dy; const T* z; int64_t ldz; T* y; int64_t ldy;
+    __device__ State init(int) const { return State{}; }
+    __device__ void load(int64_t r, int col, In& in) const {
+        in.d = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + col));
+        in.z = ldg4<T>(z + r * ldz + col);
+    }
+    __device__ void compute(const State&, int64_t r, int col, const In& in, float4* o) const {
+        const float4 v = make_float4(in.d.x * dsiluf_(in.z.x), in.d.y * dsiluf_(in.z.y), in.d.z * dsiluf_(in.z.z), in.d.w * dsiluf_(in.z.w));
+        store4<T>(y + r * ldy + col, v);
+        o[0] = v;
+    }
+};
 struct NodeBwdF {
     static constexpr int NV = 2;
     static constexpr bool F32_PARTIAL = false;
@@ -491,6 +510,36 @@ segment_sum_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restri
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     store4<TO>(out + (int64_t)node * ldo + col, acc);
+}
+
+// Few, long segments (per-crystal sums over nodes: 64 segments of ~200 rows): one block per (segment, 128-column chunk),
+// 8 row lanes that each add every 8th row in order, combined in a fixed order -- instead of one thread column walking
+// a whole segment. Deterministic; identity row order only.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+segment_sum_wide_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ ptr, int C, TO* __restrict__ out,
+                        int64_t ldo) {
+    __shared__ float4 sm[8][32];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int seg = blockIdx.x, col = blockIdx.y * 128 + lane * 4;
+    const int k0 = ptr[seg], k1 = ptr[seg + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < C) {
+        for (int k = k0 + rl; k < k1; k += 8) {
+            const float4 v = load4<T>(x + (int64_t)k * ldx + col);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    sm[rl][lane] = acc;
+    __syncthreads();
+    if (rl == 0 && col < C) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+            const float4 v = sm[q][lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        store4<TO>(out + (int64_t)seg * ldo + col, acc);
+    }
 }
 
 // Both transposed lifts in one pass: out[n, 0:C] = sum over the dst-CSR row of n of x[k, :], out[n, C:2C] = sum over the
@@ -815,6 +864,17 @@ int cartnet_segment_sum(const void* x, int64_t ldx, const int32_t* ptr, const in
     if (num_nodes <= 0) return 0;
     const int npb = 256 / (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!perm && (int64_t)num_nodes * (C / 4) <= 16384) {      // too few thread columns to fill the GPU: split the rows instead
+        const dim3 grid((unsigned)num_nodes, (unsigned)ceil_div(C, 128));
+        CN_DISPATCH_PREC(prec, {
+            if (out_is_t)
+                segment_sum_wide_kernel<T, T><<<grid, 256, 0, st>>>((const T*)x, ldx, ptr, C, (T*)out, ldo);
+            else
+                segment_sum_wide_kernel<T, float><<<grid, 256, 0, st>>>((const T*)x, ldx, ptr, C, (float*)out, ldo);
+        });
+        CN_LAUNCH_CHECK();
+        return 0;
+    }
     CN_DISPATCH_PREC(prec, {
         if (out_is_t)
             segment_sum_kernel<T, T><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, ptr, perm, num_nodes, C, (T*)out, ldo);
@@ -844,14 +904,23 @@ int cartnet_segment_sum_pair(const void* x, int64_t ldx, const int32_t* row_ptr,
 }
 
 int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy, int64_t rows,
-                      int32_t C, int32_t prec, cartnet_stream_t stream) {
-    if (rows <= 0) return 0;
+                      int32_t C, int32_t prec, float* colsum, double* partial, cartnet_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows <= 0) {
+        if (colsum) CN_CUDA(cudaMemsetAsync(colsum, 0, (size_t)C * sizeof(float), st));
+        return 0;
+    }
     CN_CHECK_ARG(dy && z && y && C % 4 == 0 && ld_dy % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "dsilu_mul: bad arguments");
-    if (rows <= 0) return 0;
+    if (colsum) {      // one pass: the column sums of y ride along (fp64 partials, fixed order)
+        CN_CHECK_ARG(partial && colreduce_shape_ok(C), "dsilu_mul: column sums need a workspace and C/4 a power of two <= 256 (C=%d)", C);
+        CN_DISPATCH_PREC(prec, {
+            DsiluMulF<T> f{dy, ld_dy, (const T*)z, ldz, (T*)y, ldy};
+            return run_colreduce(f, rows, C, partial, FIN_SUMS, colsum, nullptr, nullptr, nullptr, 0.f, C, st);
+        });
+    }
     const int64_t total = rows * (C / 4);
     CN_DISPATCH_PREC(prec, {
-        dsilu_mul_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-            dy, ld_dy, (const T*)z, ldz, (T*)y, ldy, rows, C);
+        dsilu_mul_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(dy, ld_dy, (const T*)z, ldz, (T*)y, ldy, rows, C);
     });
     CN_LAUNCH_CHECK();
     return 0;

@@ -125,20 +125,52 @@ sgemm_kernel(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, 
 }
 
 // C_b[m', n] = sum_z partial[z][m][n]  (fixed order -> deterministic); rows are split into equal blocks b = m / rows_per_blk
-// with their own destination base (the wgrad of a row-packed weight goes straight into the reference's layout)
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, TnDst dst, int64_t ldc) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // over M*N/4
+// with their own destination base (the wgrad of a row-packed weight goes straight into the reference's layout).
+// A block owns 32 consecutive float4 outputs; its 8 warps each sum a contiguous range of the splits (loads of different
+// splits are independent, 148 of them in sequence per thread made this latency-bound), then warp 0 adds the 8 range
+// sums in a fixed order.
+constexpr int SKR_GROUPS = 8;
+__global__ void __launch_bounds__(32 * SKR_GROUPS)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, TnDst dst, int64_t ldc) {
+    __shared__ float4 sm[SKR_GROUPS][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x * (int64_t)32 + lane;                   // over M*N/4
     const int64_t total4 = (int64_t)M * N / 4;
-    if (i >= total4) return;
     const int64_t lin = i * 4;
-    const int m = (int)(lin / N), n = (int)(lin % N);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int z = 0; z < splits; ++z) {
-        float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)z * M * N + lin);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (i < total4) {
+        const int per = (splits + SKR_GROUPS - 1) / SKR_GROUPS;
+        const int z0 = grp * per, z1 = (z0 + per) < splits ? (z0 + per) : splits;
+        const float* p = partial + lin;
+        const int64_t zs = (int64_t)M * N;
+        int z = z0;
+        for (; z + 4 <= z1; z += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p + (int64_t)z * zs));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(z + 1) * zs));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(z + 2) * zs));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(z + 3) * zs));
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+            s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        }
+        for (; z < z1; ++z) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p + (int64_t)z * zs));
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
     }
-    const int blk = m / dst.rows_per_blk;
-    *reinterpret_cast<float4*>(dst.c[blk] + (int64_t)(m - blk * dst.rows_per_blk) * ldc + n) = s;
+    sm[grp][lane] = s;
+    __syncthreads();
+    if (grp == 0 && i < total4) {
+#pragma unroll
+        for (int g = 1; g < SKR_GROUPS; ++g) {
+            const float4 v = sm[g][lane];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const int m = (int)(lin / N), n = (int)(lin % N);
+        const int blk = m / dst.rows_per_blk;
+        *reinterpret_cast<float4*>(dst.c[blk] + (int64_t)(m - blk * dst.rows_per_blk) * ldc + n) = s;
+    }
 }
 
 static int simt_tn_splits(int M, int N, int64_t K) {
@@ -151,7 +183,7 @@ static int simt_tn_splits(int M, int N, int64_t K) {
 
 int launch_splitk_reduce(const float* partial, int splits, int M, int N, const TnDst& dst, int64_t ldc, cudaStream_t st) {
     const int64_t total4 = (int64_t)M * N / 4;
-    splitk_reduce_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(partial, splits, M, N, dst, ldc);
+    splitk_reduce_kernel<<<(unsigned)ceil_div64(total4, 32), 32 * SKR_GROUPS, 0, st>>>(partial, splits, M, N, dst, ldc);
     CN_LAUNCH_CHECK();
     return 0;
 }

@@ -61,9 +61,8 @@ class _EdgeEncoderFn(torch.autograd.Function):
         feat, Z1, H1, Z2, Wb = ctx.saved_tensors
         prec = ctx.prec
         T = t_dtype(prec)
-        dz2 = ops.dsilu_mul(de0.contiguous(), Z2, prec)                 # [E, D]
+        dz2, dbb = ops.dsilu_mul(de0.contiguous(), Z2, prec, want_colsum=True)     # [E, D]; sum_e dz2 from the same pass
         dWb = ops.gemm_tn(prec, dz2, H1)                                # [D, 2D]
-        dbb = ops.colsum(dz2, prec)
         dz1 = torch.empty_like(Z1)
         ops.gemm(prec, dz2, _to_t(Wb.t(), prec), act=ACT_MUL_DSILU, z_in=Z1, out_t=dz1)
         dWa_full = ops.gemm_tn(prec, dz1, feat)                         # [2D, KF]
@@ -104,12 +103,11 @@ class _LinearSiluFn(torch.autograd.Function):
     def backward(ctx, dy):
         x_t, Z, W = ctx.saved_tensors
         gp = ctx.gp
-        dz = ops.dsilu_mul(dy.contiguous(), Z, gp)                      # [M, N]
+        dz, db = ops.dsilu_mul(dy.contiguous(), Z, gp, want_colsum=True)      # [M, N]; the bias gradient from the same pass
         if dz.shape[1] % 256 != 0 and x_t.shape[1] % 256 == 0:
             dW = ops.gemm_tn(gp, x_t, dz).t()                           # [K, N]^T: the tcgen05 TN kernel owns 256-row blocks
         else:
             dW = ops.gemm_tn(gp, dz, x_t)                               # [N, K]
-        db = ops.colsum(dz, gp)
         dx = torch.empty(x_t.shape[0], x_t.shape[1], dtype=torch.float32, device=dy.device)
         ops.gemm(gp, dz, _to_t(W.t(), gp), out_f32=dx)
         return dx, dW, db, None
@@ -312,7 +310,9 @@ class _NativeLayerFn(torch.autograd.Function):
         x_out = torch.empty(N, D, dtype=torch.float32, device=dev)
         e_out = torch.empty(E, D, dtype=torch.float32, device=dev)
         x_out_t = torch.empty(N, D, dtype=T, device=dev) if shadow else None
-        e_out_t = torch.empty(E, D, dtype=T, device=dev) if shadow else None
+        # the T-typed copy of e' only feeds the next layer's GEMMs: the model's last layer skips the 2 B/element store
+        want_e_t = shadow and bool(cfg.get("want_e_operand", True))
+        e_out_t = torch.empty(E, D, dtype=T, device=dev) if want_e_t else None
         part = ops._partial(dev, int(lib.cartnet_colstats_workspace(2 * D)))
         L = _lib.LayerDesc()
         L.prec, L.training, L.use_envelope, L.D = prec, int(training), int(bool(cfg["use_envelope"])), D
@@ -333,7 +333,7 @@ class _NativeLayerFn(torch.autograd.Function):
         _lib.check(lib.cartnet_layer_pack_weights(C.byref(L), st), "layer_pack_weights")
         _lib.check(lib.cartnet_layer_fwd(C.byref(L), st), "layer_fwd")
         cfg["holder"]["x_t"] = x_out_t if shadow else x_out
-        cfg["holder"]["e_t"] = e_out_t if shadow else e_out
+        cfg["holder"]["e_t"] = e_out_t if shadow else e_out      # None when skipped: a later consumer casts on demand
         ctx.set_materialize_grads(False)     # an unused edge_attr output arrives as None in backward, not as zeros
         ctx.L = L
         ctx.params = tuple(params.values())      # the Parameters themselves: backward may write straight into their .grad

@@ -443,13 +443,20 @@ def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes: int, out, prec: i
     return out
 
 
-def dsilu_mul(dy, z, prec: int) -> torch.Tensor:
+def dsilu_mul(dy, z, prec: int, want_colsum: bool = False):
+    """y = (T)(dy * silu'(z)); with want_colsum also the column sums of y (fp32 [C]) from the same pass."""
     lib = _lib.load()
     _req(dy, torch.float32, "dy"); _req(z, t_dtype(prec), "z")
     rows, Cc = int(z.shape[0]), int(z.shape[1])
     y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=z.device)
-    _lib.check(lib.cartnet_dsilu_mul(_p(dy), _ld2(dy), _p(z), _ld2(z), _p(y), Cc, rows, Cc, prec, _stream()), "dsilu_mul")
-    return y
+    tpr = Cc // 4
+    if want_colsum and Cc % 4 == 0 and 1 <= tpr <= 256 and tpr & (tpr - 1) == 0:
+        cs = torch.empty(Cc, dtype=torch.float32, device=z.device)
+        part = _partial(z.device, int(lib.cartnet_colstats_workspace(Cc)))
+        _lib.check(lib.cartnet_dsilu_mul(_p(dy), _ld2(dy), _p(z), _ld2(z), _p(y), Cc, rows, Cc, prec, _p(cs), _p(part), _stream()), "dsilu_mul")
+        return y, cs
+    _lib.check(lib.cartnet_dsilu_mul(_p(dy), _ld2(dy), _p(z), _ld2(z), _p(y), Cc, rows, Cc, prec, None, None, _stream()), "dsilu_mul")
+    return (y, colsum(y, prec)) if want_colsum else y
 
 
 def cast(x, prec: int) -> torch.Tensor:

@@ -263,9 +263,12 @@ int cartnet_segment_sum_pair(const void* x, int64_t ldx, const int32_t* row_ptr,
                              const int32_t* perm_src, int32_t num_nodes, int32_t C, void* out, int64_t ldo,
                              int32_t out_is_t, int32_t prec, cartnet_stream_t stream);
 
-/* y_t = (T)(dy * silu'(z)) elementwise over [rows, C]; dy fp32 (ld_dy), z T (ldz), y T (ldy). */
+/* y_t = (T)(dy * silu'(z)) elementwise over [rows, C]; dy fp32 (ld_dy), z T (ldz), y T (ldy). Optional colsum [C]:
+ * the column sums of y (the bias gradient of the Linear in front of the SiLU) taken in the same pass
+ * (partial >= cartnet_colstats_workspace(C) bytes, C/4 a power of two <= 256); null = plain elementwise pass. */
 int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz, void* y, int64_t ldy,
-                      int64_t rows, int32_t C, int32_t prec, cartnet_stream_t stream);
+                      int64_t rows, int32_t C, int32_t prec, float* colsum, double* partial,
+                      cartnet_stream_t stream);
 
 /* dst_t = (T) src  over [rows, C]. */
 int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C,

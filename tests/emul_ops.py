@@ -215,8 +215,10 @@ def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes, out, prec):
     return out
 
 
-def dsilu_mul(dy, z, prec):
-    return (_f(dy) * _dsilu(_f(z))).to(t_dtype(prec))
+def dsilu_mul(dy, z, prec, want_colsum=False):
+    v = _f(dy) * _dsilu(_f(z))
+    y = _shadow(v.float(), prec) if prec == PREC_TF32 else v.to(t_dtype(prec))
+    return (y, v.double().sum(0).float()) if want_colsum else y
 
 
 def cast(x, prec):

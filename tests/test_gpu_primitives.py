@@ -289,6 +289,8 @@ def test_elementwise(prec):
     dy, z = rnd(777, 512, seed=1), rnd(777, 512, seed=2).to(T)
     ref, got = both("dsilu_mul", (dy, z, prec))
     assert common.rel_err(got.float(), ref.float()) < (2e-6 if prec == PREC_FP32 else 8e-3)
+    (ref2, cs_ref), (got2, cs) = both("dsilu_mul", (dy, z, prec), dict(want_colsum=True))     # bias gradient from the same pass
+    assert torch.equal(got2, got) and common.rel_err(cs, cs_ref) < 1e-5
     ref, got = both("cast", (dy, prec))
     assert torch.equal(got.cpu(), ref)
 
