@@ -451,45 +451,82 @@ __global__ void node_bwd_apply_kernel(const float* __restrict__ dx, const float*
     *reinterpret_cast<float4*>(dm + o) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
-// dg = w * rstd * (dghat - [train](sum1/E + gn * sum2/E)). Each thread owns 4 fixed columns (coefficients hoisted)
-// and walks rows with a grid stride, 4 rows of loads in flight.
+// 16-byte vectors of the operand type: 8 bf16 / 4 fp32 words per thread and instruction
+template <typename T> struct Vec16 {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const T* p, float* v) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
+    static __device__ __forceinline__ void store(T* p, const float* v) { store4<T>(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// dg = w * rstd * (dghat - [train](sum1/E + gn * sum2/E)). Each thread owns one 16-byte column group (coefficients
+// hoisted); a block walks a CONTIGUOUS range of rows, U row groups (U x 256 threads x 16 B per tensor) in flight, so that
+// every request is a full line and consecutive requests stay in one DRAM page.
 template <typename T>
 __global__ void __launch_bounds__(256)
 edge_bwd_apply_kernel(const T* __restrict__ gn, const T* __restrict__ dghat, int64_t rows, int D, const float* var,
-                      const float* w, float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t) {
-    constexpr int U = 4;
-    const int tpr = D >> 2, lanes = 256 / tpr;
-    const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * 4;
-    float sc[4], c1[4], c2[4];
+                      const float* w, float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t,
+                      int64_t rows_per_block) {
+    constexpr int U = 4, V = Vec16<T>::N;
+    const int tpr = D / V, lanes = 256 / tpr;
+    const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * V;
+    float sc[V], c1[V], c2[V];
     const float inv_n = 1.0f / (float)rows;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
         sc[j] = (w ? w[col + j] : 1.0f) * (1.0f / sqrtf(var[col + j] + eps));
         c1[j] = training ? sums[col + j] * inv_n : 0.f;
         c2[j] = training ? sums[D + col + j] * inv_n : 0.f;
     }
-    const int64_t stride = (int64_t)gridDim.x * lanes;
-    int64_t r = (int64_t)blockIdx.x * lanes + rl;
-    for (; r + (U - 1) * stride < rows; r += U * stride) {
-        float4 h[U], d[U];
+    const int64_t r0 = blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    int64_t r = r0 + rl;
+    for (; r + (int64_t)(U - 1) * lanes < r1; r += (int64_t)U * lanes) {
+        float h[U][V], d[U][V];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t o = (r + u * stride) * D + col;
-            h[u] = ldg4<T>(gn + o);
-            d[u] = ldg4<T>(dghat + o);
+            const int64_t o = (r + (int64_t)u * lanes) * D + col;
+            Vec16<T>::load(gn + o, h[u]);
+            Vec16<T>::load(dghat + o, d[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t o = (r + u * stride) * D + col;
-            store4<T>(dg_t + o, make_float4(sc[0] * (d[u].x - (c1[0] + h[u].x * c2[0])), sc[1] * (d[u].y - (c1[1] + h[u].y * c2[1])),
-                                            sc[2] * (d[u].z - (c1[2] + h[u].z * c2[2])), sc[3] * (d[u].w - (c1[3] + h[u].w * c2[3]))));
+            float o4[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) o4[j] = sc[j] * (d[u][j] - (c1[j] + h[u][j] * c2[j]));
+            Vec16<T>::store(dg_t + (r + (int64_t)u * lanes) * D + col, o4);
         }
     }
-    for (; r < rows; r += stride) {
-        const int64_t o = r * D + col;
-        const float4 h = ldg4<T>(gn + o), d = ldg4<T>(dghat + o);
-        store4<T>(dg_t + o, make_float4(sc[0] * (d.x - (c1[0] + h.x * c2[0])), sc[1] * (d.y - (c1[1] + h.y * c2[1])),
-                                        sc[2] * (d.z - (c1[2] + h.z * c2[2])), sc[3] * (d.w - (c1[3] + h.w * c2[3]))));
+    for (; r < r1; r += lanes) {
+        float h[V], d[V], o4[V];
+        Vec16<T>::load(gn + r * D + col, h);
+        Vec16<T>::load(dghat + r * D + col, d);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o4[j] = sc[j] * (d[j] - (c1[j] + h[j] * c2[j]));
+        Vec16<T>::store(dg_t + r * D + col, o4);
     }
 }
 
@@ -846,12 +883,15 @@ int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t n
     CN_CHECK_ARG(gn_t && dghat_t && bn_var && dg_t && row_shape_ok(D), "edge_gate_bwd_apply: bad arguments");
     CN_CHECK_ARG(!training || sums, "edge_gate_bwd_apply: sums required in training mode");
     if (num_edges <= 0) return 0;
-    const int lanes = 256 / (D / 4);
-    int64_t blocks = ceil_div64(num_edges, (int64_t)lanes * 8);
-    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     CN_DISPATCH_PREC(prec, {
+        constexpr int V = Vec16<T>::N;
+        CN_CHECK_ARG(D % V == 0 && 256 % (D / V) == 0, "edge_gate_bwd_apply: unsupported D=%d", D);
+        const int lanes = 256 / (D / V);
+        // contiguous row ranges, a multiple of one unrolled batch (4 x lanes rows); 3 blocks per SM = one resident wave at 66 registers
+        int64_t per = ceil_div64(ceil_div64(num_edges, (int64_t)3 * kNumSMs), (int64_t)4 * lanes) * 4 * lanes;
+        const int64_t blocks = ceil_div64(num_edges, per);
         edge_bwd_apply_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            (const T*)gn_t, (const T*)dghat_t, num_edges, D, bn_var, bn_weight, eps, sums, training, (T*)dg_t);
+            (const T*)gn_t, (const T*)dghat_t, num_edges, D, bn_var, bn_weight, eps, sums, training, (T*)dg_t, per);
     });
     CN_LAUNCH_CHECK();
     return 0;
