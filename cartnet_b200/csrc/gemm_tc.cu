@@ -545,6 +545,7 @@ tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         for (int h = 0; h < 2; ++h) {
             const int row = mb * TN_MBLK + h * 128 + q * 32 + lane;
+            if (mb * TN_MBLK + h * 128 >= M) break;        // M = odd multiple of 128: the last block's second half is TMA zero fill
             float* dst = partial + ((int64_t)split * M + row) * N + (int64_t)nb * Nblk;
             for (int c = 0; c < Nblk; c += 32) {
                 float v[32];
@@ -684,11 +685,11 @@ struct TnPlan {
 };
 static bool tn_plan(int prec, int M, int N, int64_t K, TnPlan* p) {
     const int boxw = prec == CARTNET_PREC_BF16 ? 64 : 32;
-    if (M % TN_MBLK != 0 || N % boxw != 0) return false;
+    if (M % 128 != 0 || N % boxw != 0) return false;      // rows beyond M inside the last 256-row block are zero-filled by TMA
     p->Nblk = N <= 256 ? N : 256;
     if (N % p->Nblk != 0 || p->Nblk % 32 != 0 || p->Nblk % 16 != 0) return false;
     p->n_blocks = N / p->Nblk;
-    p->m_blocks = M / TN_MBLK;
+    p->m_blocks = ceil_div(M, TN_MBLK);
     p->kblks_total = (int)ceil_div64(K > 0 ? K : 1, boxw);      // KROWS == boxw for both types
     const int problems = p->n_blocks * p->m_blocks;
     int s = kNumSMs / problems;
@@ -712,7 +713,7 @@ static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda,
     using TR = TcTraits<T>;
     const int esize = (int)sizeof(T);
     TnPlan p;
-    CN_CHECK_ARG(tn_plan(prec, M, N, K, &p), "tcgen05 gemm_tn: unsupported shape M=%d N=%d (need M %% 256 == 0, N %% %d == 0)", M, N, TR::KB);
+    CN_CHECK_ARG(tn_plan(prec, M, N, K, &p), "tcgen05 gemm_tn: unsupported shape M=%d N=%d (need M %% 128 == 0, N %% %d == 0)", M, N, TR::KB);
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, TR::DT, esize, A, K, M, lda, TR::KB, TR::KB, TR::MN_SWIZZLE);
     if (rc) return rc;

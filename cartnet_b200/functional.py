@@ -104,8 +104,8 @@ class _LinearSiluFn(torch.autograd.Function):
         x_t, Z, W = ctx.saved_tensors
         gp = ctx.gp
         dz, db = ops.dsilu_mul(dy.contiguous(), Z, gp, want_colsum=True)      # [M, N]; the bias gradient from the same pass
-        if dz.shape[1] % 256 != 0 and x_t.shape[1] % 256 == 0:
-            dW = ops.gemm_tn(gp, x_t, dz).t()                           # [K, N]^T: the tcgen05 TN kernel owns 256-row blocks
+        if dz.shape[1] % 128 != 0 and x_t.shape[1] % 128 == 0:
+            dW = ops.gemm_tn(gp, x_t, dz).t()                           # [K, N]^T: the tcgen05 TN kernel owns 128-row accumulators
         else:
             dW = ops.gemm_tn(gp, dz, x_t)                               # [N, K]
         dx = torch.empty(x_t.shape[0], x_t.shape[1], dtype=torch.float32, device=dy.device)

@@ -279,3 +279,27 @@ def test_direct_gradient_writes_are_bit_identical():
         flats.append(sync.flat.clone())
         assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())
     assert torch.equal(flats[0], flats[1])
+
+
+@pytest.mark.parametrize("dim_in,layers", [(128, 2), (512, 1)])
+def test_other_hidden_widths(dim_in, layers):
+    """`--dim_in` other than the default 256 (main.py:141): every kernel shape constraint holds for multiples of 128
+    (weight-gradient GEMM on single 128-row accumulators, narrower resident weight slices, D/2-wide head)."""
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
+    batch_cpu = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes))
+    torch.manual_seed(0)
+    orc = O.OracleCartNet(dim_in, 64, layers, **kw)
+    sd = fixtures.make_state_dict(orc.state_dict(), seed)
+    orc.load_state_dict(sd)
+    ref = common.run_train_step(orc, batch_cpu)
+    for precision, tol_train, tol_eval in (("fp32", 2e-5, 1e-5), ("bf16", 1e-1, 5e-3)):
+        model = cartnet_b200.CartNet(dim_in, 64, layers, precision=precision, **kw)
+        model.load_state_dict(sd)
+        model.cuda()
+        got = common.run_train_step(model, batch_cpu.clone().to("cuda"))
+        assert common.rel_err(got["pred"], ref["pred"]) < tol_train, precision
+        assert common.rel_err(got["pred_eval"], ref["pred_eval"]) < tol_eval, precision
+        if precision == "fp32":
+            scale = max(float(v.abs().max()) for v in ref["grads"].values())
+            for k, g in ref["grads"].items():
+                assert float((got["grads"][k].cpu() - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-5 * scale, k
