@@ -10,7 +10,7 @@ Every function cites the reference lines it restates (paths relative to
 ("parity unpinned" upstream), so this oracle is pinned against outputs
 of the UNMODIFIED reference files run in the authoring container through
 oracle/ref_loader.py; the vectors live in tests/golden/ and were produced by
-scripts/make_golden.py.
+tests/golden/make_golden.py.
 
 Two parts:
   * graph build  -- numpy, explicit fp32, no FMA, chunked over destination rows so it

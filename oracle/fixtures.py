@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- seeded inputs and weights shared by scripts/make_golden.py,
+"""TEST INFRASTRUCTURE ONLY -- seeded inputs and weights shared by tests/golden/make_golden.py,
 tests/ and the smoke / cpu_baseline legs. Graphs here are built with the ORACLE graph
 builder (never the CUDA one) so that model parity does not depend on graph parity."""
 from __future__ import annotations

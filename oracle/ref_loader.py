@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY. Imports the UNMODIFIED reference hot-path modules from
 /root/reference through the stand-ins in oracle/_shim. Only usable in the authoring
-container (the GPU box has no /root/reference); used by scripts/make_golden.py to
+container (the GPU box has no /root/reference); used by tests/golden/make_golden.py to
 generate tests/golden/*.npz and by tests that pin oracle/cartnet_oracle.py."""
 import importlib
 import os

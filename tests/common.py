@@ -4,7 +4,7 @@ import hashlib
 import numpy as np
 import torch
 
-# scripts/make_golden.py::MODEL_CASES (kept in sync by test_golden_cases_in_sync)
+# tests/golden/make_golden.py::MODEL_CASES (kept in sync by test_golden_cases_in_sync)
 MODEL_CASES = {
     "adp": ("adp", [24, 41], 21, dict(invariant=False, temperature=True, use_envelope=True,
                                        atom_types=True, cholesky=True), 5.0),

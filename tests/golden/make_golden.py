@@ -3,7 +3,7 @@
 /root/reference through oracle/ref_loader.py) on seeded synthetic inputs, and checks the
 oracle restatement (oracle/cartnet_oracle.py) against them while doing so.
 
-Run in the authoring container only:   python scripts/make_golden.py
+Run in the authoring container only:   python tests/golden/make_golden.py
 The GPU box has no /root/reference; tests there read the committed .npz files.
 """
 from __future__ import annotations
@@ -16,7 +16,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from cartnet_b200 import synthetic  # noqa: E402

@@ -46,7 +46,7 @@ def test_fp32_path_matches_reference_golden(golden_model, name):
 def test_fp32_layer_matches_reference_layer(name, training):
     """north_star, literally: "fp32 node features ... match the reference PyG LAYER within 1e-5 relative".
     Every CartNet_layer (and the edge encoder) is fed the oracle's own inputs -- the oracle is bit-identical to
-    the reference's forward (scripts/make_golden.py asserts pred error 0.0) -- and its outputs are compared
+    the reference's forward (tests/golden/make_golden.py asserts pred error 0.0) -- and its outputs are compared
     layer by layer, so rounding differences cannot compound through the four BatchNorm'd layers."""
     shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
     batch_cpu = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes), cholesky=kw["cholesky"],

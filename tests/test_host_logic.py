@@ -72,7 +72,7 @@ def test_unsorted_edges_give_same_result(monkeypatch):
 
 def test_state_dict_keys_match_reference_layout():
     m = cartnet_b200.CartNet(256, 64, 4)
-    o = O.OracleCartNet(256, 64, 4)          # keys verified == reference in scripts/make_golden.py
+    o = O.OracleCartNet(256, 64, 4)          # keys verified == reference in tests/golden/make_golden.py
     assert list(m.state_dict().keys()) == list(o.state_dict().keys())
     for k, v in o.state_dict().items():
         assert m.state_dict()[k].shape == v.shape, k

@@ -1,5 +1,5 @@
 """CPU: pins the oracle restatement against the golden vectors produced by the unmodified reference
-(scripts/make_golden.py). Runs on the GPU box too (no /root/reference needed)."""
+(tests/golden/make_golden.py). Runs on the GPU box too (no /root/reference needed)."""
 import numpy as np
 import pytest
 import torch
