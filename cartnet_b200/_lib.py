@@ -77,8 +77,8 @@ SIGNATURES = {
     "cartnet_node_update": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, f32, vp, vp, i32, vp]),
     "cartnet_node_update_bwd_reduce": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp]),
     "cartnet_node_update_bwd_apply": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, f32, vp, i32, vp, vp]),
-    "cartnet_edge_gate_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, f32, i32, vp, vp, i32, vp, vp, vp]),
-    "cartnet_edge_gate_bwd_apply": (i32, [vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, i32, vp]),
+    "cartnet_edge_gate_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, f32, i32, vp, vp, i32, vp, vp, vp, vp, f32, vp]),
+    "cartnet_edge_gate_bwd_apply": (i32, [vp, vp, i64, i32, vp, vp, f32, vp, i32, vp, i32, vp, i32, vp]),
     "cartnet_segment_sum": (i32, [vp, i64, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "cartnet_segment_sum_pair": (i32, [vp, i64, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "cartnet_dsilu_mul": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
             acc[v][0] += (double)val[v].x; acc[v][1] += (double)val[v].y; acc[v][2] += (double)val[v].z; acc[v][3] += (double)val[v].w;
         }
     }
+    f.finish(col, acc);                      // per-column fix-up of the thread's totals (a no-op for most functors)
     double* mine = sm + (size_t)rl * NV * C;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -207,6 +208,7 @@ struct StatsF {
         o[0] = a;
         o[1] = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
     }
+    __device__ void finish(int, double (*)[4]) const {}
 };
 template <typename TX>
 struct SumF {
@@ -218,6 +220,7 @@ struct SumF {
     __device__ State init(int) const { return State{}; }
     __device__ void load(int64_t r, int col, In& in) const { in = load4<TX>(x + r * ld + col); }
     __device__ void compute(const State&, int64_t, int, const In& a, float4* o) const { o[0] = a; }
+    __device__ void finish(int, double (*)[4]) const {}
 };
 // y = (T)(dy * silu'(z)) written on the fly, column sums of y (a bias gradient) as the reduction
 template <typename T>
@@ -237,6 +240,7 @@ struct DsiluMulF {
         store4<T>(y + r * ldy + col, v);
         o[0] = v;
     }
+    __device__ void finish(int, double (*)[4]) const {}
 };
 struct NodeBwdF {
     static constexpr int NV = 2;
@@ -256,6 +260,7 @@ struct NodeBwdF {
         o[0] = a;
         o[1] = make_float4(a.x * h.x, a.y * h.y, a.z * h.z, a.w * h.w);
     }
+    __device__ void finish(int, double (*)[4]) const {}
 };
 // FAST: MUFU-based sigmoid / cosine for the tensor-core modes (their operands carry >= 2^-11 rounding anyway);
 // the fp32 parity mode keeps expf / cosf / IEEE division.
@@ -278,11 +283,32 @@ struct EdgeBwdF {
     const T *gn, *s; const float* dist; const int32_t* dst; const float *de, *dm; int D;
     const float *w, *bias; float radius; int use_env;
     T *ds_t, *dghat_t;
+    // gvar != null: `gn` holds the stored (centred) pre-activation g, gn = (g - gmean) * rsqrt(gvar + eps) (gmean null = 0)
+    // -- the forward pass then need not write a normalised copy. The affine BN(g) = gn w + b is folded into the
+    // per-column constants (no extra registers in the row loop); the second sum is taken over dghat * g and turned into
+    // sum dghat * gn = rstd (sum dghat g - mean sum dghat) once per thread in finish(), on the fp64 totals.
+    const float *gmean, *gvar; float eps;
     __device__ State init(int col) const {
         State c;
         c.w = w ? *reinterpret_cast<const float4*>(w + col) : make_float4(1.f, 1.f, 1.f, 1.f);
         c.b = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gvar) {
+            const float4 v = *reinterpret_cast<const float4*>(gvar + col);
+            const float4 mu = gmean ? *reinterpret_cast<const float4*>(gmean + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 rs = make_float4(1.0f / sqrtf(v.x + eps), 1.0f / sqrtf(v.y + eps), 1.0f / sqrtf(v.z + eps), 1.0f / sqrtf(v.w + eps));
+            c.w = make_float4(c.w.x * rs.x, c.w.y * rs.y, c.w.z * rs.z, c.w.w * rs.w);
+            c.b = make_float4(c.b.x - mu.x * c.w.x, c.b.y - mu.y * c.w.y, c.b.z - mu.z * c.w.z, c.b.w - mu.w * c.w.w);
+        }
         return c;
+    }
+    __device__ void finish(int col, double (*acc)[4]) const {
+        if (!gvar) return;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double rs = 1.0 / sqrt((double)gvar[col + j] + (double)eps);
+            const double mu = gmean ? (double)gmean[col + j] : 0.0;
+            acc[1][j] = rs * (acc[1][j] - mu * acc[0][j]);
+        }
     }
     __device__ void load(int64_t r, int col, In& in) const {
         // read-only (non-coherent) loads of U rows are all in flight before the first store
@@ -489,7 +515,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 edge_bwd_apply_kernel(const T* __restrict__ gn, const T* __restrict__ dghat, int64_t rows, int D, const float* var,
                       const float* w, float eps, const float* __restrict__ sums, int training, T* __restrict__ dg_t,
-                      int64_t rows_per_block) {
+                      int64_t rows_per_block, const float* gmean, int input_is_g) {
     constexpr int U = 4, V = Vec16<T>::N;
     const int tpr = D / V, lanes = 256 / tpr;
     const int rl = threadIdx.x / tpr, col = (threadIdx.x % tpr) * V;
@@ -497,9 +523,14 @@ edge_bwd_apply_kernel(const T* __restrict__ gn, const T* __restrict__ dghat, int
     const float inv_n = 1.0f / (float)rows;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        sc[j] = (w ? w[col + j] : 1.0f) * (1.0f / sqrtf(var[col + j] + eps));
+        const float rstd = 1.0f / sqrtf(var[col + j] + eps);
+        sc[j] = (w ? w[col + j] : 1.0f) * rstd;
         c1[j] = training ? sums[col + j] * inv_n : 0.f;
         c2[j] = training ? sums[D + col + j] * inv_n : 0.f;
+        if (input_is_g) {      // the tensor holds the stored (centred) g: gn * c2 = (g - mean) * rstd * c2
+            c1[j] -= (gmean ? gmean[col + j] : 0.f) * rstd * c2[j];
+            c2[j] *= rstd;
+        }
     }
     const int64_t r0 = blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
@@ -859,19 +890,19 @@ int cartnet_edge_gate_bwd_reduce(const void* gn_t, const void* s_t, const float*
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
                                  const float* bn_weight, const float* bn_bias, float radius, int32_t use_envelope,
                                  void* ds_t, void* dghat_t, int32_t prec, float* sums, double* partial,
-                                 cartnet_stream_t stream) {
+                                 const float* g_mean, const float* g_var, float eps, cartnet_stream_t stream) {
     CN_CHECK_ARG(gn_t && s_t && dist && dst32 && dm && ds_t && dghat_t && sums && partial && num_edges > 0,
                  "edge_gate_bwd_reduce: bad arguments");
     CN_CHECK_ARG(colreduce_shape_ok(D), "edge_gate_bwd_reduce: unsupported D=%d", D);
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == CARTNET_PREC_FP32) {
         EdgeBwdF<float, false> f{(const float*)gn_t, (const float*)s_t, dist, dst32, de_out, dm, D, bn_weight, bn_bias, radius,
-                                 use_envelope, (float*)ds_t, (float*)dghat_t};
+                                 use_envelope, (float*)ds_t, (float*)dghat_t, g_mean, g_var, eps};
         return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
     }
     CN_DISPATCH_PREC(prec, {
         EdgeBwdF<T, true> f{(const T*)gn_t, (const T*)s_t, dist, dst32, de_out, dm, D, bn_weight, bn_bias, radius, use_envelope,
-                            (T*)ds_t, (T*)dghat_t};
+                            (T*)ds_t, (T*)dghat_t, g_mean, g_var, eps};
         return run_colreduce(f, num_edges, D, partial, FIN_SUMS, sums, nullptr, nullptr, nullptr, 0.f, 3 * D, st);
     });
     return 0;
@@ -879,7 +910,7 @@ int cartnet_edge_gate_bwd_reduce(const void* gn_t, const void* s_t, const float*
 
 int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t num_edges, int32_t D, const float* bn_var,
                                 const float* bn_weight, float eps, const float* sums, int32_t training, void* dg_t,
-                                int32_t prec, cartnet_stream_t stream) {
+                                int32_t prec, const float* g_mean, int32_t input_is_g, cartnet_stream_t stream) {
     CN_CHECK_ARG(gn_t && dghat_t && bn_var && dg_t && row_shape_ok(D), "edge_gate_bwd_apply: bad arguments");
     CN_CHECK_ARG(!training || sums, "edge_gate_bwd_apply: sums required in training mode");
     if (num_edges <= 0) return 0;
@@ -891,7 +922,7 @@ int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t n
         int64_t per = ceil_div64(ceil_div64(num_edges, (int64_t)3 * kNumSMs), (int64_t)4 * lanes) * 4 * lanes;
         const int64_t blocks = ceil_div64(num_edges, per);
         edge_bwd_apply_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            (const T*)gn_t, (const T*)dghat_t, num_edges, D, bn_var, bn_weight, eps, sums, training, (T*)dg_t, per);
+            (const T*)gn_t, (const T*)dghat_t, num_edges, D, bn_var, bn_weight, eps, sums, training, (T*)dg_t, per, g_mean, input_is_g);
     });
     CN_LAUNCH_CHECK();
     return 0;

@@ -161,9 +161,15 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     CN_TRY(cartnet_node_update_bwd_reduce(L->dx_out, L->m, N, D, mean2, var2, L->bn2_w, L->bn2_b, L->eps, L->sums2, L->partial, st));
     CN_TRY(cartnet_node_update_bwd_apply(L->dx_out, L->m, N, D, mean2, var2, L->bn2_w, L->bn2_b, L->eps, L->sums2, L->training, L->dm, st));
     // edge side: sig = env * sigmoid(BN1(g)); e' = e + sig; m = segsum(sig * s)
-    CN_TRY(cartnet_edge_gate_bwd_reduce(L->gn_t, L->s_t, L->dist, L->dst32, L->de_out, L->dm, E, D, L->bn1_w, L->bn1_b, L->radius,
-                                        L->use_envelope, L->ds_t, L->dghat_t, prec, L->sums1, L->partial, st));
-    CN_TRY(cartnet_edge_gate_bwd_apply(L->gn_t, L->dghat_t, E, D, var1, L->bn1_w, L->eps, L->sums1, L->training, L->dg_t, prec, st));
+    // gn_t null: the forward pass kept the centred pre-activation g_t instead of writing a normalised copy; the backward
+    // kernels normalise on the fly (training: batch mean of the stored values; eval: g_t is centred on the running mean)
+    const void* gsrc = L->gn_t ? L->gn_t : L->g_t;
+    const float* gmean = (!L->gn_t && L->training) ? L->mean1 : nullptr;
+    const float* gvar = L->gn_t ? nullptr : var1;
+    CN_TRY(cartnet_edge_gate_bwd_reduce(gsrc, L->s_t, L->dist, L->dst32, L->de_out, L->dm, E, D, L->bn1_w, L->bn1_b, L->radius,
+                                        L->use_envelope, L->ds_t, L->dghat_t, prec, L->sums1, L->partial, gmean, gvar, L->eps, st));
+    CN_TRY(cartnet_edge_gate_bwd_apply(gsrc, L->dghat_t, E, D, var1, L->bn1_w, L->eps, L->sums1, L->training, L->dg_t, prec, gmean,
+                                       L->gn_t ? 0 : 1, st));
     bias_grad_kernel<<<ceil_div(D, 128), 128, 0, (cudaStream_t)st>>>(L->sums1, L->sums2, L->bn1_w, var1, L->eps, L->training, D, L->dba2,
                                                                       L->dbg2, L->dbn1_w, L->dbn1_b, L->dbn2_w, L->dbn2_b);
     CN_LAUNCH_CHECK();

@@ -185,8 +185,9 @@ class _LayerFn(torch.autograd.Function):
             else:
                 ops.gemm(prec, H[:, :D], G2_t, bias=bias_c, out_t=g)
             ops.gemm(prec, H[:, D:], A2_t, bias=ba2.detach(), out_t=s)
-        e_out, e_out_t, m, gn = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
-                                                        b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True)
+        # no normalised copy of g is written: the backward kernels normalise the stored (centred) g on the fly
+        e_out, e_out_t, m, _ = ops.edge_gate_aggregate(g, s, e, dist, plan.row_ptr, N, mean1, var1, w1.detach(),
+                                                       b1n.detach(), cfg["radius"], cfg["use_envelope"], prec, True, want_gn=False)
         if training:
             mean2, var2 = ops.colstats(m, cfg["rm2"], cfg["rv2"], cfg["momentum2"])
         else:
@@ -194,9 +195,9 @@ class _LayerFn(torch.autograd.Function):
         x_out, x_out_t = ops.node_update(m, x, mean2, var2, w2.detach(), b2n.detach(), prec, True)   # cartnet.py:269,223
         cfg["holder"]["x_t"], cfg["holder"]["e_t"] = x_out_t, e_out_t
 
-        ctx.save_for_backward(x_t, e_t, Z, H, gn, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
+        ctx.save_for_backward(x_t, e_t, Z, H, g, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
         ctx.cfg = dict(prec=prec, plan=plan, dist=dist, training=training, radius=cfg["radius"],
-                       use_envelope=cfg["use_envelope"])
+                       use_envelope=cfg["use_envelope"], mean1=mean1)
         return x_out, e_out
 
     @staticmethod
@@ -219,7 +220,7 @@ class _LayerFn(torch.autograd.Function):
         dm, sums2 = ops.node_update_bwd(dx_out, m, mean2, var2, w2, b2n, training)
         # edge side: sig = env * sigmoid(BN1(g)); e' = e + sig; m = segsum(sig * s)
         ds_t, dg_t, sums1 = ops.edge_gate_bwd(gn, s, c["dist"], plan.dst32, de_out, dm, var1, w1, b1n,
-                                              c["radius"], c["use_envelope"], training, prec)
+                                              c["radius"], c["use_envelope"], training, prec, g_mean=c["mean1"], input_is_g=True)
         # second Linears: dgrad (+ SiLU') and wgrad
         dZ = torch.empty(E, 2 * D, dtype=T, device=dev)
         ops.gemm(prec, dg_t, _to_t(G2.t(), prec), act=ACT_MUL_DSILU, z_in=Z[:, :D], out_t=dZ[:, :D])
@@ -300,9 +301,9 @@ class _NativeLayerFn(torch.autograd.Function):
             e_t = ops.cast(e, prec)
         shadow = needs_shadow(prec)
         DD = D * D
-        g_t = torch.empty(E, D, dtype=T, device=dev)                 # centred gate pre-activation; not kept for backward
+        gn_t = None                                                  # no normalised copy: backward reads the centred g_t
         tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D + 2 * E * D, dtype=T, device=dev)
-        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H, s_t, gn_t) = _carve(tbuf, [
+        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H, s_t, g_t) = _carve(tbuf, [
             (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D),
             (E, D), (E, D)])
         fbuf = torch.empty(N * D + 9 * D, dtype=torch.float32, device=dev)

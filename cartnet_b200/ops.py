@@ -393,8 +393,10 @@ def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training: bool):
 
 
 def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius: float, use_envelope: bool,
-                  training: bool, prec: int):
+                  training: bool, prec: int, g_mean=None, input_is_g: bool = False):
     """gn_t, s_t: the T tensors saved by edge_gate_aggregate / the MLP_aggr GEMM. de_out may be None (= zero).
+    input_is_g: `gn_t` is the stored, centred pre-activation g itself (no normalised copy was written forward);
+    gn = (g - g_mean) * rsqrt(bn_var + eps) is formed inside the kernels (g_mean None = 0).
     Returns ds_t, dg_t (T, [E,D]) and sums [3D]: sum dghat (= d bias of the edge BatchNorm) | sum dghat*gn
     (= d weight) | sum ds (= d bias of MLP_aggr[2])."""
     lib = _lib.load()
@@ -412,9 +414,11 @@ def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius
     st = _stream()
     _lib.check(lib.cartnet_edge_gate_bwd_reduce(
         _p(gn_t), _p(s_t), _p(dist), _p(dst32), _p(de_out), _p(dm), E, D, _p(bn_w), _p(bn_b),
-        float(radius), int(bool(use_envelope)), _p(ds_t), _p(dghat_t), prec, _p(sums), _p(part), st), "edge_gate_bwd_reduce")
+        float(radius), int(bool(use_envelope)), _p(ds_t), _p(dghat_t), prec, _p(sums), _p(part),
+        _p(g_mean) if input_is_g else None, _p(bn_var) if input_is_g else None, EPS_BN, st), "edge_gate_bwd_reduce")
     _lib.check(lib.cartnet_edge_gate_bwd_apply(_p(gn_t), _p(dghat_t), E, D, _p(bn_var), _p(bn_w), EPS_BN,
-                                               _p(sums), int(bool(training)), _p(dg_t), prec, st), "edge_gate_bwd_apply")
+                                               _p(sums), int(bool(training)), _p(dg_t), prec,
+                                               _p(g_mean) if input_is_g else None, int(bool(input_is_g)), st), "edge_gate_bwd_apply")
     return ds_t, dg_t, sums
 
 

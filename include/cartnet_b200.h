@@ -239,16 +239,22 @@ int cartnet_node_update_bwd_apply(const float* dx_out, const float* m, int32_t n
  * dghat = (de_out + s * dmd) * env * sigmoid'(ghat) -> dghat_t (T);
  * sums[0:D] = sum_e dghat, sums[D:2D] = sum_e dghat * gn, sums[2D:3D] = sum_e ds (sums has 3D entries; the sums
  * are taken before the rounding to T).
- * de_out may be null (no gradient flows into e_out, e.g. the last layer: the heads read only x). */
+ * de_out may be null (no gradient flows into e_out, e.g. the last layer: the heads read only x).
+ * g_var != null: `gn_t` holds the stored, centred pre-activation g (what cartnet_gemm_colstats wrote) and
+ * gn = (g - g_mean) * rsqrt(g_var + eps) is formed on the fly (g_mean null = 0: eval mode, g centred on the running
+ * mean), so that the forward pass need not write a normalised copy. g_var null: `gn_t` is already normalised. */
 int cartnet_edge_gate_bwd_reduce(const void* gn_t, const void* s_t, const float* dist, const int32_t* dst32,
                                  const float* de_out, const float* dm, int64_t num_edges, int32_t D,
                                  const float* bn_weight, const float* bn_bias, float radius,
                                  int32_t use_envelope, void* ds_t, void* dghat_t, int32_t prec, float* sums,
-                                 double* partial, cartnet_stream_t stream);
-/* step 2: dg = weight*rstd*(dghat - [train](sum/E + gn*sum2/E)) -> dg_t (T). */
+                                 double* partial, const float* g_mean, const float* g_var, float eps,
+                                 cartnet_stream_t stream);
+/* step 2: dg = weight*rstd*(dghat - [train](sum/E + gn*sum2/E)) -> dg_t (T). input_is_g != 0: `gn_t` holds the
+ * stored g as above (normalised with g_mean, bn_var, eps). */
 int cartnet_edge_gate_bwd_apply(const void* gn_t, const void* dghat_t, int64_t num_edges, int32_t D,
                                 const float* bn_var, const float* bn_weight, float eps, const float* sums,
-                                int32_t training, void* dg_t, int32_t prec, cartnet_stream_t stream);
+                                int32_t training, void* dg_t, int32_t prec, const float* g_mean,
+                                int32_t input_is_g, cartnet_stream_t stream);
 
 /* out[n, 0:C] = sum over CSR row n of x[perm[k], 0:C] (perm may be null = identity). x is T,
  * out is T (out_is_t=1) or fp32. Used for d(P_i) (dst CSR) and d(P_j) (src CSR) -- the transpose of the
@@ -305,7 +311,7 @@ typedef struct cartnet_layer {
     void* g_t;                                       /* T [E,D]: centred gate pre-activation (scratch after the forward pass) */
     float *center, *bias_c, *hsum;                   /* [D] each: cartnet_gate_center outputs / scratch */
     float* m;                                        /* [N,D] */
-    void *s_t, *gn_t;                                /* T [E,D]: MLP_aggr output, normalised gate pre-activation (saved) */
+    void *s_t, *gn_t;                                /* T [E,D]: MLP_aggr output (saved); gn_t: optional normalised copy of g_t -- null: g_t itself is kept for backward */
     float *mean1, *var1, *mean2, *var2;              /* [D] statistics used (batch or running) */
     float *x_out, *e_out;                            /* [N,D], [E,D] */
     void *x_out_t, *e_out_t;                         /* T copies for the next layer (null when T = float) */

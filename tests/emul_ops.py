@@ -181,9 +181,12 @@ def node_update_bwd(dx_out, m, bn_mean, bn_var, bn_w, bn_b, training):
     return dm.float(), torch.cat([s1, s2]).float()
 
 
-def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius, use_envelope, training, prec):
+def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius, use_envelope, training, prec,
+                  g_mean=None, input_is_g=False):
     gn = _f(gn_t)
     rstd = 1.0 / torch.sqrt(_f(bn_var) + EPS_BN)
+    if input_is_g:           # the stored, centred pre-activation itself: normalise here
+        gn = (gn - (0.0 if g_mean is None else _f(g_mean))) * rstd
     sg = torch.sigmoid(gn * _f(bn_w) + _f(bn_b))
     env = _env(_f(dist), radius, use_envelope).unsqueeze(-1)
     dmd = _f(dm)[dst32.long()]

@@ -253,6 +253,13 @@ def test_edge_gate_bwd(prec, training, with_de):
     assert common.rel_err(got[0].float(), ref[0].float()) < t
     assert common.rel_err(got[1].float(), ref[1].float()) < t
     assert common.rel_err(got[2], ref[2]) < 1e-5
+    # the layer keeps the stored (centred) g instead of a normalised copy: the kernels normalise on the fly
+    g_mean = rnd(D, seed=6, scale=0.3) if training else None
+    kw = dict(g_mean=g_mean, input_is_g=True)
+    ref, got = both("edge_gate_bwd", (gn, s, dist, plan.dst32, de, dm, var, w, b, 5.0, True, training, prec), kw)
+    for i in range(2):
+        assert common.rel_err(got[i].float(), ref[i].float()) < t
+    assert common.rel_err(got[2], ref[2]) < 2e-5
 
 
 @pytest.mark.parametrize("prec", PRECS)
