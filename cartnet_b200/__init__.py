@@ -6,9 +6,9 @@ Importing the package does not need a GPU; calling any operator does, and raises
 CUDA library (cartnet_b200/libcartnet_b200.so) is missing -- there is no CPU fallback.
 """
 from . import augment  # noqa: F401
-from .batch import CrystalBatch, DevicePrefetcher, collate  # noqa: F401
+from .batch import CrystalBatch, DeferredScalars, DevicePrefetcher, collate  # noqa: F401
 from .cartnet import CartNet, CartNet_layer, Cholesky_head, Encoder, Scalar_head  # noqa: F401
 from .radius_graph import build_graph, radius_graph_pbc  # noqa: F401
 
 __all__ = ["CartNet", "Encoder", "CartNet_layer", "Cholesky_head", "Scalar_head", "radius_graph_pbc",
-           "build_graph", "CrystalBatch", "DevicePrefetcher", "collate"]
+           "build_graph", "CrystalBatch", "DevicePrefetcher", "DeferredScalars", "collate"]

@@ -111,10 +111,16 @@ class DevicePrefetcher:
     reference's DataLoader(pin_memory=True) + `batch.to("cuda:0")` (/root/reference/loader/loader.py:114-124,
     train/train.py:169)."""
 
+    _streams = {}      # one copy stream per device for the process: the caching allocator pools blocks per stream, so a
+                       # fresh stream per prefetcher (per epoch) would cudaMalloc its batch buffers again every time
+
     def __init__(self, batches, device):
         self.it = iter(batches)
         self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device)
+        key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device)
+        self.stream = DevicePrefetcher._streams[key]
         self._next = None
         self._preload()
 
@@ -151,3 +157,53 @@ class DevicePrefetcher:
                 v.record_stream(cur)
         self._preload()
         return b
+
+
+class DeferredScalars:
+    """Per-step scalars (loss, metrics) read back WITHOUT stalling the step that produced them: `push(t)` issues an
+    asynchronous device->host copy of a 1-element tensor into a pinned ring slot and records an event; `pop()` returns
+    the oldest pushed value as a float, waiting only for ITS copy (normally long finished). With `depth` >= 2 the host
+    keeps issuing step i+1 while step i runs, instead of draining the GPU at every `loss.item()` the way the reference's
+    per-iteration metric reads do (/root/reference/train/train.py:192-199, train/metrics.py:202-206).
+    CPU tensors are accepted (the value is copied immediately) so that host logic can be tested without a GPU."""
+
+    def __init__(self, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.depth = depth
+        self.buf = torch.zeros(depth, dtype=torch.float32)
+        if torch.cuda.is_available():
+            self.buf = self.buf.pin_memory()
+        self.events = [None] * depth
+        self.head = 0          # next slot to write
+        self.count = 0         # values pushed and not yet popped
+
+    def push(self, t: torch.Tensor):
+        """Queue a scalar; returns the oldest value (float) if the ring was full, else None."""
+        out = self.pop() if self.count == self.depth else None
+        slot = self.head
+        src = t.detach().reshape(1).to(torch.float32)
+        self.buf[slot:slot + 1].copy_(src, non_blocking=True)
+        if src.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(src.device))
+            self.events[slot] = ev
+        else:
+            self.events[slot] = None
+        self.head = (self.head + 1) % self.depth
+        self.count += 1
+        return out
+
+    def pop(self) -> float:
+        if self.count == 0:
+            raise IndexError("no pending scalar")
+        slot = (self.head - self.count) % self.depth
+        ev = self.events[slot]
+        if ev is not None:
+            ev.synchronize()
+        self.count -= 1
+        return float(self.buf[slot])
+
+    def drain(self):
+        """All pending values, oldest first."""
+        return [self.pop() for _ in range(self.count)]

@@ -123,3 +123,16 @@ def test_plan_cache_is_identity_keyed(monkeypatch):
     assert CN.get_plan(b) is p1
     b.edge_index = b.edge_index.clone()
     assert CN.get_plan(b) is not p1
+
+
+def test_deferred_scalars_ring():
+    """cartnet_b200.DeferredScalars: FIFO order, ring overflow hands back the oldest value, drain empties it."""
+    from cartnet_b200 import DeferredScalars
+    d = DeferredScalars(depth=2)
+    assert d.push(torch.tensor(1.5)) is None
+    assert d.push(torch.tensor([2.5])) is None
+    assert d.push(torch.tensor(3.5)) == 1.5          # ring full: the oldest value comes back
+    assert d.pop() == 2.5
+    assert d.drain() == [3.5]
+    with pytest.raises(IndexError):
+        d.pop()
