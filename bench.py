@@ -35,6 +35,24 @@ KB_PER_EDGE_STEP = 23.1e3        # algorithmic HBM bytes per e
 FLOP_PER_EDGE_STEP = 7.3e6       # algorithmic FLOPs per edge per step with the K=256 split
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """Rank 0 prints ONE JSON line on stdout: anything else a library writes to file descriptor 1 (NCCL's version banner
+    goes there) is sent to stderr; the JSON line is written to the saved descriptor by emit()."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: str):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -186,7 +204,7 @@ def run_reference(args):
                          "sample": "%d crystals (%d edges) of the ADP-64 batch per step" % (graphs, edges)},
         "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------- instrumented pass
@@ -274,8 +292,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 
@@ -439,7 +455,7 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -458,6 +474,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
