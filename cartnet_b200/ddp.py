@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -32,12 +34,15 @@ class FlatGradAllReduce:
     def __init__(self, params, group=None, direct: bool = False):
         """direct=True additionally lets the hand-written backward kernels store a parameter's gradient straight
         into its slice of the flat buffer (no AccumulateGrad `+=` launch per parameter). The caller promises what
-        a plain training loop does anyway: zero() before every backward and each parameter used once per
-        backward (no gradient accumulation across micro-batches, no weight sharing)."""
+        a plain training loop does anyway: zero() before every backward. A second backward without zero() in between
+        (gradient accumulation over micro-batches) is detected per parameter and falls back to autograd's accumulation,
+        and the shortcut ends with this object's lifetime."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.direct = bool(direct)
+        self.epoch = 0                     # bumped by zero(): a parameter is written directly at most once per epoch
         for p in self.params:
-            p._cn_direct_grad = bool(direct)
+            p._cn_direct_owner = weakref.ref(self) if self.direct else None
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -47,6 +52,7 @@ class FlatGradAllReduce:
             off += p.numel()
 
     def zero(self):
+        self.epoch += 1
         self.flat.zero_()
         off = 0
         for p in self.params:   # re-attach in case an optimiser / zero_grad(set_to_none=True) dropped the views

@@ -368,10 +368,13 @@ class _NativeLayerFn(torch.autograd.Function):
         grads = [dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n]
         direct = [False] * len(grads)
         for i, prm in enumerate(ctx.params):
-            tgt = prm.grad if getattr(prm, "_cn_direct_grad", False) else None
-            if (tgt is not None and tgt.is_contiguous() and tgt.dtype == torch.float32 and tgt.device == dev
-                    and tgt.shape == grads[i].shape):
+            owner = getattr(prm, "_cn_direct_owner", None)
+            owner = owner() if owner is not None else None
+            tgt = prm.grad if owner is not None and owner.direct else None
+            if (tgt is not None and getattr(prm, "_cn_written_epoch", -1) != owner.epoch and tgt.is_contiguous()
+                    and tgt.dtype == torch.float32 and tgt.device == dev and tgt.shape == grads[i].shape):
                 grads[i], direct[i] = tgt, True
+                prm._cn_written_epoch = owner.epoch      # a second backward before the next zero() accumulates via autograd
         (dG1, dA1, dbg1, dba1, dG2, dA2, dbg2, dba2, dw1, db1n, dw2, db2n) = grads
         nbytes = int(lib.cartnet_layer_splitk_bytes(prec, D, N, E))
         ws = ops._workspace(dev, nbytes)

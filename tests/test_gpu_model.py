@@ -278,6 +278,11 @@ def test_direct_gradient_writes_are_bit_identical():
             torch.nn.functional.l1_loss(pred, true).backward()
         flats.append(sync.flat.clone())
         assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())
+        if direct:      # a second backward WITHOUT zero() (gradient accumulation) must add, not overwrite
+            pred, true = model(batch0.clone())
+            torch.nn.functional.l1_loss(pred, true).backward()
+            ref2 = 2.0 * flats[0]
+            assert common.rel_err(sync.flat, ref2) < 1e-5
     assert torch.equal(flats[0], flats[1])
 
 
