@@ -438,7 +438,7 @@ def run_ours(args):
     line = {
         "metric": "graphs_per_sec", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+        "dtype": {"bf16x3": "bf16x3", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
         "edges_per_sec": world * edges_step / step_s,
         "config": {"workload": "CartNet ADP training step (fwd+bwd+Adam), batch %d crystals per GPU" % args.batch,
                    "crystals_per_gpu": args.batch, "atoms_per_gpu": nodes_step, "edges_per_gpu": edges_step, "radius": 5.0,
@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CARTNET_BENCH_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("CARTNET_BENCH_PRECISION", "bf16"), choices=["bf16x3", "bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=4, help="crystals per step for the CPU reference (bounded sample)")

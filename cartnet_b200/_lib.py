@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcartnet_b200.so")
 
-PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3 = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_MUL_DSILU = 0, 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -83,6 +83,7 @@ SIGNATURES = {
     "cartnet_segment_sum_pair": (i32, [vp, i64, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "cartnet_dsilu_mul": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),
     "cartnet_cast_rows": (i32, [vp, i64, vp, i64, i64, i32, i32, vp]),
+    "cartnet_uncast_rows": (i32, [vp, i64, vp, i64, i64, i32, i32, vp]),
     "cartnet_layer_splitk_bytes": (i64, [i32, i32, i32, i64]),
     "cartnet_layer_pack_weights": (i32, [C.POINTER(LayerDesc), vp]),
     "cartnet_layer_fwd": (i32, [C.POINTER(LayerDesc), vp]),

@@ -24,9 +24,9 @@ import torch.nn.functional as F
 
 from . import functional as CF
 from . import ops
-from .ops import PREC_BF16, PREC_FP32, PREC_TF32
+from .ops import PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32
 
-_PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
+_PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}
 
 
 def default_precision() -> str:

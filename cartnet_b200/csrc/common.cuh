@@ -67,6 +67,38 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
+// Storage type of the split-precision mode (CARTNET_PREC_BF16X3): every element occupies 4 bytes, but the words are
+// not individually meaningful. Each run of 64 consecutive elements (256 bytes, 256-byte aligned) holds the 64 bf16 HIGH
+// parts (128 bytes) followed by the 64 bf16 LOW parts: value = hi + lo with hi = bf16(v), lo = bf16(v - hi), i.e. ~16
+// mantissa bits. Seen as a bf16 matrix of twice the width, the hi / lo halves of a chunk are two 128-byte TMA boxes,
+// which is what lets tcgen05 contract a pair tensor with three kind::f16 MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulate).
+// Pointer arithmetic on bf16p_t* is in ELEMENTS, exactly like float*; the helpers below map an element address to the
+// addresses of its two halves. Requirements: 256-byte aligned bases, row pitches and column offsets multiples of 64.
+struct bf16p_t { uint32_t raw; };
+__device__ __forceinline__ char* pair_hi_addr(const void* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    return reinterpret_cast<char*>((a & ~(uintptr_t)255) + ((a & (uintptr_t)255) >> 1));      // lo half: + 128
+}
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float2 bf162_to_float2(uint32_t w) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+// 4 floats -> hi (2 words) and lo (2 words) bf16 pairs
+__device__ __forceinline__ void split4_bf16(const float4& v, uint2& hi, uint2& lo) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+__device__ __forceinline__ float4 join4_bf16(const uint2& hi, const uint2& lo) {
+    const float2 a = bf162_to_float2(hi.x), b = bf162_to_float2(hi.y), c = bf162_to_float2(lo.x), d = bf162_to_float2(lo.y);
+    return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+}
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -86,6 +118,18 @@ __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// one element at an element address (weight packing; not a hot path)
+template <typename T>
+__device__ __forceinline__ void store1(T* p, float v) { *p = from_f32<T>(v); }
+template <>
+__device__ __forceinline__ void store1<bf16p_t>(bf16p_t* p, float v) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    char* h = pair_hi_addr(p);
+    *reinterpret_cast<__nv_bfloat16*>(h) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(h + 128) = lo;
+}
+
 // 4 consecutive elements, 16-byte (float) / 8-byte (bf16) aligned
 template <typename T>
 __device__ __forceinline__ float4 load4(const T* p);
@@ -101,6 +145,11 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
 }
 template <>
 __device__ __forceinline__ float4 load4<tf32_t>(const tf32_t* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<bf16p_t>(const bf16p_t* p) {
+    const char* h = pair_hi_addr(p);
+    return join4_bf16(*reinterpret_cast<const uint2*>(h), *reinterpret_cast<const uint2*>(h + 128));
+}
 // read-only (non-coherent) variants: the compiler may hoist them above unrelated stores
 template <typename T>
 __device__ __forceinline__ float4 ldg4(const T* p);
@@ -116,15 +165,27 @@ __device__ __forceinline__ float4 ldg4<__nv_bfloat16>(const __nv_bfloat16* p) {
     float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
     return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+template <>
+__device__ __forceinline__ float4 ldg4<bf16p_t>(const bf16p_t* p) {
+    const char* h = pair_hi_addr(p);
+    return join4_bf16(__ldg(reinterpret_cast<const uint2*>(h)), __ldg(reinterpret_cast<const uint2*>(h + 128)));
+}
 // raw (unconverted) 4-element loads so that all global reads of a chunk can be issued before any math / store
 template <typename T> struct Raw4;
 template <> struct Raw4<tf32_t> { using type = float4; };
 template <> struct Raw4<float> { using type = float4; };
 template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+template <> struct Raw4<bf16p_t> { using type = uint4; };      // {hi.x, hi.y, lo.x, lo.y}
 template <typename T> __device__ __forceinline__ typename Raw4<T>::type ld_raw4(const T* p);
 template <> __device__ __forceinline__ float4 ld_raw4<tf32_t>(const tf32_t* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 template <> __device__ __forceinline__ float4 ld_raw4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 template <> __device__ __forceinline__ uint2 ld_raw4<__nv_bfloat16>(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+template <> __device__ __forceinline__ uint4 ld_raw4<bf16p_t>(const bf16p_t* p) {
+    const char* h = pair_hi_addr(p);
+    const uint2 hi = __ldg(reinterpret_cast<const uint2*>(h)), lo = __ldg(reinterpret_cast<const uint2*>(h + 128));
+    return make_uint4(hi.x, hi.y, lo.x, lo.y);
+}
+__device__ __forceinline__ float4 cvt_raw4(const uint4& r) { return join4_bf16(make_uint2(r.x, r.y), make_uint2(r.z, r.w)); }
 __device__ __forceinline__ float4 cvt_raw4(const float4& r) { return r; }
 __device__ __forceinline__ float4 cvt_raw4(const uint2& r) {
     const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
@@ -151,6 +212,15 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v
     *reinterpret_cast<uint2*>(p) = r;
 }
 
+template <>
+__device__ __forceinline__ void store4<bf16p_t>(bf16p_t* p, float4 v) {
+    uint2 hi, lo;
+    split4_bf16(v, hi, lo);
+    char* h = pair_hi_addr(p);
+    *reinterpret_cast<uint2*>(h) = hi;
+    *reinterpret_cast<uint2*>(h + 128) = lo;
+}
+
 // ---- activations (full-precision expf: the fp32 path is held to 1e-5) -------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 __device__ __forceinline__ float siluf_(float v) { return v * sigmoidf_(v); }
@@ -175,6 +245,9 @@ __device__ __forceinline__ float cosine_cutoff(float d, float upper) {
             __VA_ARGS__                                                     \
         } else if ((prec) == CARTNET_PREC_TF32) {                           \
             using T = cartnet::tf32_t;                                      \
+            __VA_ARGS__                                                     \
+        } else if ((prec) == CARTNET_PREC_BF16X3) {                         \
+            using T = cartnet::bf16p_t;                                     \
             __VA_ARGS__                                                     \
         } else {                                                            \
             cartnet::set_error("unknown prec %d", (int)(prec));             \

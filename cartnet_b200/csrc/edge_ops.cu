@@ -486,6 +486,14 @@ template <typename T> struct Vec16 {
     }
     static __device__ __forceinline__ void store(T* p, const float* v) { store4<T>(p, make_float4(v[0], v[1], v[2], v[3])); }
 };
+template <> struct Vec16<bf16p_t> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const bf16p_t* p, float* v) {
+        const float4 r = ldg4<bf16p_t>(p);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
+    static __device__ __forceinline__ void store(bf16p_t* p, const float* v) { store4<bf16p_t>(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int N = 8;
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
@@ -676,6 +684,17 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t lds, T* 
     store4<T>(dst + r * ldd + col, *reinterpret_cast<const float4*>(src + r * lds + col));
 }
 
+template <typename T>
+__global__ void uncast_rows_kernel(const T* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                                   int64_t rows, int C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c4 = C >> 2;
+    if (i >= rows * c4) return;
+    const int64_t r = i / c4;
+    const int col = (int)(i % c4) * 4;
+    *reinterpret_cast<float4*>(dst + r * ldd + col) = load4<T>(src + r * lds + col);
+}
+
 // feat[e, :] = [ cut(d) exp(-beta_k (exp(-alpha d) - mu_k)^2) (k < R) ; cart_dir (3, unless invariant) ; 1 ; 0 ... ]
 // The first padding column (if ld leaves one) holds 1: the matching column of the zero-padded weight is 0, so the forward
 // is unchanged, while in the backward the bias gradient sum_e dz falls out of the weight-gradient GEMM dz^T feat as that
@@ -759,6 +778,10 @@ int cartnet_colstats(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, 
         StatsF<__nv_bfloat16> f{(const __nv_bfloat16*)x, ld};
         return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0, st, shift);
     }
+    if (x_is_t && prec == CARTNET_PREC_BF16X3) {
+        StatsF<bf16p_t> f{(const bf16p_t*)x, ld};
+        return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0, st, shift);
+    }
     StatsF<float> f{(const float*)x, ld};
     return run_colreduce(f, rows, C, partial, FIN_STATS, mean, var, running_mean, running_var, momentum, 0, st, shift);
 }
@@ -789,6 +812,10 @@ int cartnet_colsum(const void* x, int32_t x_is_t, int32_t prec, int64_t rows, in
     cudaStream_t st = (cudaStream_t)stream;
     if (x_is_t && prec == CARTNET_PREC_BF16) {
         SumF<__nv_bfloat16> f{(const __nv_bfloat16*)x, ld};
+        return run_colreduce(f, rows, C, partial, FIN_SUMS, out, nullptr, nullptr, nullptr, 0.f, C, st);
+    }
+    if (x_is_t && prec == CARTNET_PREC_BF16X3) {
+        SumF<bf16p_t> f{(const bf16p_t*)x, ld};
         return run_colreduce(f, rows, C, partial, FIN_SUMS, out, nullptr, nullptr, nullptr, 0.f, C, st);
     }
     SumF<float> f{(const float*)x, ld};
@@ -1005,6 +1032,18 @@ int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int
     const int64_t total = rows * (C / 4);
     CN_DISPATCH_PREC(prec, {
         cast_rows_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (T*)dst, ldd, rows, C);
+    });
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_uncast_rows(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t C, int32_t prec,
+                        cartnet_stream_t stream) {
+    if (rows <= 0) return 0;
+    CN_CHECK_ARG(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "uncast_rows: bad arguments");
+    const int64_t total = rows * (C / 4);
+    CN_DISPATCH_PREC(prec, {
+        uncast_rows_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, lds, dst, ldd, rows, C);
     });
     CN_LAUNCH_CHECK();
     return 0;

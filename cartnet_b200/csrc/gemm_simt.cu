@@ -205,7 +205,7 @@ int cartnet_gemm(const cartnet_gemm_t* d, cartnet_stream_t stream) {
     CN_CHECK_ARG(d->out_f32 || d->out_t || d->z_out, "gemm: no output");
     if (d->M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->prec == CARTNET_PREC_BF16 || d->prec == CARTNET_PREC_TF32) return gemm_tc_nt(*d, st);
+    if (d->prec != CARTNET_PREC_FP32 && d->prec >= 0 && d->prec <= CARTNET_PREC_BF16X3) return gemm_tc_nt(*d, st);
     CN_CHECK_ARG(d->prec == CARTNET_PREC_FP32, "gemm: unknown prec %d", d->prec);
     const int n_tiles = ceil_div(d->N, BN);
     const int64_t tiles = (int64_t)ceil_div(d->M, BM) * n_tiles;
@@ -223,7 +223,7 @@ int cartnet_gemm_colstats(const cartnet_gemm_t* d, const float* shift, float* me
     CN_CHECK_ARG(mean && var && partial && d->M > 0, "gemm_colstats: bad arguments");
     CN_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "gemm_colstats: running stats must come in pairs");
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->prec == CARTNET_PREC_BF16 || d->prec == CARTNET_PREC_TF32) {
+    if (d->prec != CARTNET_PREC_FP32 && d->prec >= 0 && d->prec <= CARTNET_PREC_BF16X3) {
         CN_CHECK_ARG(d->A && d->B && d->bias && d->N > 0 && d->K > 0, "gemm_colstats: bad GEMM arguments");
         int blocks = 0;
         if (int rc = gemm_tc_nt(*d, st, partial, &blocks)) return rc;       // sums ride in the epilogue
@@ -235,7 +235,7 @@ int cartnet_gemm_colstats(const cartnet_gemm_t* d, const float* shift, float* me
 }
 
 int64_t cartnet_gemm_tn_workspace(int32_t prec, int32_t M, int32_t N, int64_t K) {
-    if (prec == CARTNET_PREC_BF16 || prec == CARTNET_PREC_TF32) return gemm_tc_tn_workspace(prec, M, N, K);
+    if (prec != CARTNET_PREC_FP32 && prec >= 0 && prec <= CARTNET_PREC_BF16X3) return gemm_tc_tn_workspace(prec, M, N, K);
     return (int64_t)simt_tn_splits(M, N, K) * M * N * (int64_t)sizeof(float);
 }
 
@@ -253,7 +253,7 @@ int cartnet_gemm_tn_blocks(int32_t prec, int32_t M, int32_t N, int64_t K, const 
         dst.c[b] = C_blocks[b];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (prec == CARTNET_PREC_BF16 || prec == CARTNET_PREC_TF32)
+    if (prec != CARTNET_PREC_FP32 && prec >= 0 && prec <= CARTNET_PREC_BF16X3)
         return gemm_tc_tn(prec, M, N, K, A, lda, B, ldb, dst, ldc, workspace, workspace_bytes, st);
     CN_CHECK_ARG(prec == CARTNET_PREC_FP32, "gemm_tn: unknown prec %d", prec);
     if (K <= 0) {

@@ -132,8 +132,27 @@ struct TcTraits<__nv_bfloat16> {
     static constexpr int UMMA_K = 16;
     static constexpr int FMT = 1;
     static constexpr bool TF32 = false;
+    static constexpr int NP = 1;         // operand parts per element (2 = hi | lo bf16 pair)
+    static constexpr int TMA_ES = 2;     // bytes per element as TMA sees the tensor
+    static constexpr int TN_KROWS = 64;  // k rows per TN pipeline stage
     static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     // MN-major operands (TN kernel): canonical SWIZZLE_128B atom = 8 k rows x 128 B
+    static constexpr uint32_t MN_LAYOUT = 2, MN_SBO = 1024;
+    static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B;
+};
+// Split precision (CARTNET_PREC_BF16X3): the tensor is a bf16 matrix of twice the logical width in which every 64-element
+// chunk is [64 hi | 64 lo] (common.cuh::bf16p_t); a K block (or an MN box) of 64 elements is two 128-byte TMA boxes, and
+// a product costs three kind::f16 MMAs into the same fp32 accumulator: hi*hi + hi*lo + lo*hi (lo*lo ~ 2^-18 is dropped).
+template <>
+struct TcTraits<bf16p_t> {
+    static constexpr int KB = 64;
+    static constexpr int UMMA_K = 16;
+    static constexpr int FMT = 1;
+    static constexpr bool TF32 = false;
+    static constexpr int NP = 2;
+    static constexpr int TMA_ES = 2;
+    static constexpr int TN_KROWS = 32;
+    static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     static constexpr uint32_t MN_LAYOUT = 2, MN_SBO = 1024;
     static constexpr CUtensorMapSwizzle MN_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B;
 };
@@ -143,6 +162,9 @@ struct TcTraits<tf32_t> {
     static constexpr int UMMA_K = 8;
     static constexpr int FMT = 2;
     static constexpr bool TF32 = true;
+    static constexpr int NP = 1;
+    static constexpr int TMA_ES = 4;
+    static constexpr int TN_KROWS = 32;
     static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     // 32-bit MN-major operands only exist as SWIZZLE_128B_BASE32B (Swizzle<2,5,2>): atom = 4 k rows x 128 B,
     // 32-byte chunks XORed with the row index; TMA writes it with SWIZZLE_128B_ATOM_32B
@@ -219,11 +241,11 @@ __device__ __forceinline__ void stats_flush(float* wstat, int cidx, int lane, fl
 }
 
 // ------------------------------------------------------------------------------------------ NT kernel
-constexpr int NT_STAGES = 3;
-constexpr int NT_A_STAGE_BYTES = 128 * 128;      // 128 rows x 128 B
+constexpr int NT_STAGES = 3;                     // at most; the host picks 2 when the operands are pairs and the weight slice is large
+constexpr int NT_A_PART_BYTES = 128 * 128;       // 128 rows x 128 B (one operand part of one K block)
 constexpr int NT_EPI_WARPS = 8;
 constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
-constexpr int NT_STG_PITCH = 36;                                  // floats; 144 B rows keep float4 accesses conflict-minimal
+constexpr int NT_STG_PITCH = 32;                                  // floats; 16-byte chunks XOR-swizzled with the row: conflict-free float4 accesses both ways
 constexpr int NT_STG_BYTES = NT_EPI_WARPS * 32 * NT_STG_PITCH * 4;   // per-warp 32x32 fp32 transpose buffers
 
 struct NtBars {
@@ -235,15 +257,19 @@ constexpr int NT_STAT_BYTES = NT_EPI_WARPS * 2 * 128 * 4;          // per-warp [
 template <typename T, int EPI>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-             int BN, int n_tiles, int m_tiles, EpiParams<T> epi, double* __restrict__ stats) {
+             int BN, int n_tiles, int m_tiles, int stages, EpiParams<T> epi, double* __restrict__ stats) {
     using TR = TcTraits<T>;
+    constexpr int NP = TR::NP;
+    constexpr int KBOX = 128 / TR::TMA_ES;           // TMA elements per 128-byte box row
+    constexpr int A_STAGE_BYTES = NP * NT_A_PART_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int kblks = K / TR::KB;
-    const int b_kb_bytes = BN * 128;
+    const int b_part_bytes = BN * 128;
+    const int b_kb_bytes = NP * b_part_bytes;
     uint8_t* smemB = smem;
     uint8_t* smemA = smem + (size_t)kblks * b_kb_bytes;
-    float* smemStg = reinterpret_cast<float*>(smemA + NT_STAGES * NT_A_STAGE_BYTES);
+    float* smemStg = reinterpret_cast<float*>(smemA + stages * A_STAGE_BYTES);
     NtBars* bars = reinterpret_cast<NtBars*>(reinterpret_cast<uint8_t*>(smemStg) + NT_STG_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,7 +281,9 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (threadIdx.x == 0) {
         for (int s = 0; s < NT_STAGES; ++s) { mbar_init(&bars->a_full[s], 1); mbar_init(&bars->a_empty[s], 1); }
         mbar_init(&bars->b_full, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], NT_EPI_WARPS); }
+        // BN <= 32: only the first column group (4 warps) has columns; idle warps must not arrive (they would run ahead
+        // of the MMA warp and complete phases it has not waited for yet)
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], BN > 32 ? NT_EPI_WARPS : NT_EPI_WARPS / 2); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&bars->tmem_slot, tmem_cols);
@@ -268,15 +296,20 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             mbar_expect_tx(&bars->b_full, (uint32_t)(kblks * b_kb_bytes));
-            for (int kb = 0; kb < kblks; ++kb) tma_load_2d(smemB + (size_t)kb * b_kb_bytes, &tmB, kb * TR::KB, n0, &bars->b_full);
+            for (int kb = 0; kb < kblks; ++kb)
+#pragma unroll
+                for (int pt = 0; pt < NP; ++pt)
+                    tma_load_2d(smemB + (size_t)kb * b_kb_bytes + pt * b_part_bytes, &tmB, (kb * NP + pt) * KBOX, n0, &bars->b_full);
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_stride) {
                 for (int kb = 0; kb < kblks; ++kb) {
                     mbar_wait(&bars->a_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bars->a_full[stage], NT_A_STAGE_BYTES);
-                    tma_load_2d(smemA + stage * NT_A_STAGE_BYTES, &tmA, kb * TR::KB, mt * 128, &bars->a_full[stage]);
-                    if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+                    mbar_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
+#pragma unroll
+                    for (int pt = 0; pt < NP; ++pt)
+                        tma_load_2d(smemA + stage * A_STAGE_BYTES + pt * NT_A_PART_BYTES, &tmA, (kb * NP + pt) * KBOX, mt * 128, &bars->a_full[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -293,19 +326,27 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 mbar_wait(&bars->a_full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(smemA + stage * NT_A_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(smemA + stage * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(smemB + (size_t)kb * b_kb_bytes);
 #pragma unroll
                     for (int j = 0; j < TR::KB / TR::UMMA_K; ++j) {   // 4 MMAs of K = 32 bytes inside the swizzle row
                         const uint64_t ad = smem_desc(a_addr + j * 32, 16, 1024);
                         const uint64_t bd = smem_desc(b_addr + j * 32, 16, 1024);
-                        tc_mma<TR::TF32>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        if (NP == 2) {      // split precision: the two cross terms first, then hi*hi, all into one fp32 accumulator
+                            const uint64_t al = smem_desc(a_addr + NT_A_PART_BYTES + j * 32, 16, 1024);
+                            const uint64_t bl = smem_desc(b_addr + b_part_bytes + j * 32, 16, 1024);
+                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), al, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), ad, bl, idesc, 1u);
+                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, 1u);
+                        } else {
+                            tc_mma<TR::TF32>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        }
                     }
                     tc_commit(&bars->a_empty[stage]);                  // frees the A stage when the MMAs retire
                     if (kb == kblks - 1) tc_commit(&bars->tmem_full[acc]);
                 }
                 __syncwarp();
-                if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -333,7 +374,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int mt = m_first; mt < m_tiles; mt += m_stride) {
+        for (int mt = m_first; mt < m_tiles && c_begin < c_end; mt += m_stride) {
             const int64_t row0 = (int64_t)mt * 128 + q * 32;
             // gather-row indices of the 8 output rows this thread finishes (hoisted out of the column loop)
             int32_t i0[8], i1[8];
@@ -393,11 +434,14 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 float4 t4[8];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) t4[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * NT_STG_PITCH + sub_c);
+                for (int it = 0; it < 8; ++it) {
+                    const int srow = it * 4 + sub_r;
+                    t4[it] = *reinterpret_cast<const float4*>(stg + srow * NT_STG_PITCH + 4 * ((sub_c >> 2) ^ (srow & 7)));
+                }
                 __syncwarp();
                 float4 ss = zero, sq = zero;
                 if (full) {
@@ -467,15 +511,18 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t K, int M, int N,
              int Nblk, int n_blocks, int kblks_total, int kblks_per_split, float* __restrict__ partial) {
     using TR = TcTraits<T>;
+    constexpr int NP = TR::NP;
     constexpr int BOXW = TR::KB;                    // mn elements per 128-byte row
-    constexpr int KROWS = TR::KB;                   // k rows per stage: 64 (bf16) / 32 (tf32)
+    constexpr int KROWS = TR::TN_KROWS;             // k rows per stage: 64 (bf16) / 32 (tf32, bf16 pairs)
     constexpr int BOX_BYTES = KROWS * 128;
     constexpr int A_BOXES = TN_MBLK / BOXW;
-    constexpr int A_BYTES = A_BOXES * BOX_BYTES;    // 32 KB
+    constexpr int A_PART_BYTES = A_BOXES * BOX_BYTES;
+    constexpr int A_BYTES = NP * A_PART_BYTES;      // 32 KB
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_boxes = Nblk / BOXW;
-    const int stage_bytes = A_BYTES + b_boxes * BOX_BYTES;
+    const int b_part_bytes = b_boxes * BOX_BYTES;
+    const int stage_bytes = A_BYTES + NP * b_part_bytes;
     TnBars* bars = reinterpret_cast<TnBars*>(smem + (size_t)TN_STAGES * stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -506,8 +553,14 @@ tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 uint8_t* sb = sa + A_BYTES;
-                for (int i = 0; i < A_BOXES; ++i) tma_load_2d(sa + i * BOX_BYTES, &tmA, mb * TN_MBLK + i * BOXW, kb * KROWS, &bars->full[stage]);
-                for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * BOX_BYTES, &tmB, nb * Nblk + i * BOXW, kb * KROWS, &bars->full[stage]);
+                // pairs: element column c (a multiple of 64) = bf16 columns [2c, 2c+64) (hi) and [2c+64, 2c+128) (lo)
+#pragma unroll
+                for (int pt = 0; pt < NP; ++pt) {
+                    for (int i = 0; i < A_BOXES; ++i)
+                        tma_load_2d(sa + pt * A_PART_BYTES + i * BOX_BYTES, &tmA, NP * (mb * TN_MBLK + i * BOXW) + pt * BOXW, kb * KROWS, &bars->full[stage]);
+                    for (int i = 0; i < b_boxes; ++i)
+                        tma_load_2d(sb + pt * b_part_bytes + i * BOX_BYTES, &tmB, NP * (nb * Nblk + i * BOXW) + pt * BOXW, kb * KROWS, &bars->full[stage]);
+                }
                 if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -529,8 +582,17 @@ tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t bd = smem_desc(b_addr + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint64_t ad = smem_desc(a_addr + h * (A_BYTES / 2) + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
-                        tc_mma<TR::TF32>(tmem_base + (uint32_t)(h * Nblk), ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        const uint64_t ad = smem_desc(a_addr + h * (A_PART_BYTES / 2) + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
+                        const uint32_t first = (kb > kb0 || j > 0) ? 1u : 0u;
+                        if (NP == 2) {
+                            const uint64_t al = smem_desc(a_addr + A_PART_BYTES + h * (A_PART_BYTES / 2) + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
+                            const uint64_t bl = smem_desc(b_addr + b_part_bytes + koff, BOX_BYTES, TR::MN_SBO, TR::MN_LAYOUT);
+                            tc_mma<false>(tmem_base + (uint32_t)(h * Nblk), al, bd, idesc, first);
+                            tc_mma<false>(tmem_base + (uint32_t)(h * Nblk), ad, bl, idesc, 1u);
+                            tc_mma<false>(tmem_base + (uint32_t)(h * Nblk), ad, bd, idesc, 1u);
+                        } else {
+                            tc_mma<TR::TF32>(tmem_base + (uint32_t)(h * Nblk), ad, bd, idesc, first);
+                        }
                     }
                 }
                 tc_commit(&bars->empty[stage]);
@@ -612,25 +674,36 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const v
 template <typename T>
 static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks) {
     using TR = TcTraits<T>;
-    const int esize = (int)sizeof(T);
+    constexpr int NP = TR::NP;
+    const int slot = (int)sizeof(T);          // shared-memory bytes per operand element (pairs: hi + lo)
     CN_CHECK_ARG(d.K % TR::KB == 0, "tcgen05 gemm: K=%d must be a multiple of %d", d.K, TR::KB);
-    // resident weight slice: largest BN with BN*K*esize <= 128 KB that divides N
-    int BN = 0;
+    if (NP == 2) {
+        CN_CHECK_ARG((reinterpret_cast<uintptr_t>(d.A) & 255) == 0 && (reinterpret_cast<uintptr_t>(d.B) & 255) == 0 && d.lda % 64 == 0 && d.ldb % 64 == 0,
+                     "tcgen05 gemm: bf16x3 operands need 256-byte aligned bases and row pitches that are multiples of 64");
+    }
+    // resident weight slice: largest BN with BN*K*slot <= 128 KB that divides N and leaves room for >= 2 A stages
+    int BN = 0, stages = 0;
+    size_t smem = 0;
     static const int bn_cap = getenv("CARTNET_NT_BN_CAP") ? atoi(getenv("CARTNET_NT_BN_CAP")) : 256;   // tuning knob (experiments)
-    for (int cand : {256, 128, 64, 32})
-        if (cand <= bn_cap && (int64_t)cand * d.K * esize <= 131072 && d.N % cand == 0) { BN = cand; break; }
+    for (int cand : {256, 128, 64, 32}) {
+        if (cand > bn_cap || (int64_t)cand * d.K * slot > 131072 || d.N % cand != 0) continue;
+        for (int ns : {NT_STAGES, 2}) {
+            const size_t need = 1024 + (size_t)cand * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
+                                (stats ? NT_STAT_BYTES : 0);
+            if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; break; }
+        }
+        if (BN) break;
+    }
     CN_CHECK_ARG(BN > 0, "tcgen05 gemm: no resident tile for N=%d K=%d", d.N, d.K);
     const int n_tiles = d.N / BN, m_tiles = ceil_div(d.M, 128);
     CN_CHECK_ARG(n_tiles <= kNumSMs, "tcgen05 gemm: too many N tiles (%d)", n_tiles);
     int grid = (kNumSMs / n_tiles) * n_tiles;
     if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, TR::DT, esize, d.A, d.M, d.K, d.lda, TR::KB, 128);
+    int rc = make_map(&tmA, TR::DT, TR::TMA_ES, d.A, d.M, (int64_t)NP * d.K, NP * d.lda, 128 / TR::TMA_ES, 128);
     if (rc) return rc;
-    rc = make_map(&tmB, TR::DT, esize, d.B, d.N, d.K, d.ldb, TR::KB, BN);
+    rc = make_map(&tmB, TR::DT, TR::TMA_ES, d.B, d.N, (int64_t)NP * d.K, NP * d.ldb, 128 / TR::TMA_ES, BN);
     if (rc) return rc;
-    const size_t smem = 1024 + (size_t)BN * d.K * esize + NT_STAGES * NT_A_STAGE_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
-                        (stats ? NT_STAT_BYTES : 0);
     if (stats_blocks) *stats_blocks = (grid / n_tiles) * 4;
     int mask = 0;
     if (stats) mask |= EB_STATS;
@@ -648,7 +721,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     if (mask == (M_)) {                                                                                              \
         static bool attr_done[64] = {};                                                                              \
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_)>, attr_done)) return rc_;                                 \
-        tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi, stats); \
+        tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, stages, epi, stats); \
         CN_LAUNCH_CHECK();                                                                                           \
         return 0;                                                                                                    \
     }
@@ -668,7 +741,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     {
         static bool attr_done[64] = {};
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, EPI_GENERIC>, attr_done)) return rc_;
-        tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, epi, nullptr);
+        tc_nt_kernel<T, EPI_GENERIC><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, stages, epi, nullptr);
         CN_LAUNCH_CHECK();
     }
     return 0;
@@ -677,6 +750,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
 // stats: optional fp64 partial buffer [stats_blocks][2][N] (sum | sum of squares of the output columns)
 int gemm_tc_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks) {
     if (d.prec == CARTNET_PREC_BF16) return run_nt<__nv_bfloat16>(d, st, stats, stats_blocks);
+    if (d.prec == CARTNET_PREC_BF16X3) return run_nt<bf16p_t>(d, st, stats, stats_blocks);
     return run_nt<tf32_t>(d, st, stats, stats_blocks);
 }
 
@@ -684,16 +758,17 @@ struct TnPlan {
     int Nblk, n_blocks, m_blocks, kblks_total, kblks_per_split, splits;
 };
 static bool tn_plan(int prec, int M, int N, int64_t K, TnPlan* p) {
-    const int boxw = prec == CARTNET_PREC_BF16 ? 64 : 32;
+    const int boxw = prec == CARTNET_PREC_TF32 ? 32 : 64;           // mn elements per TMA box
+    const int krows = prec == CARTNET_PREC_BF16 ? 64 : 32;          // k rows per pipeline stage (TcTraits::TN_KROWS)
     if (M % 128 != 0 || N % boxw != 0) return false;      // rows beyond M inside the last 256-row block are zero-filled by TMA
     p->Nblk = N <= 256 ? N : 256;
     if (N % p->Nblk != 0 || p->Nblk % 32 != 0 || p->Nblk % 16 != 0) return false;
     p->n_blocks = N / p->Nblk;
     p->m_blocks = ceil_div(M, TN_MBLK);
-    p->kblks_total = (int)ceil_div64(K > 0 ? K : 1, boxw);      // KROWS == boxw for both types
+    p->kblks_total = (int)ceil_div64(K > 0 ? K : 1, krows);
     const int problems = p->n_blocks * p->m_blocks;
     int s = kNumSMs / problems;
-    const int by_k = p->kblks_total / 16;          // at least 16 k-blocks per split: partials must not outweigh the operands
+    const int by_k = p->kblks_total / (1024 / krows);   // at least 1024 k rows per split: partials must not outweigh the operands
     if (s > by_k) s = by_k;
     if (s < 1) s = 1;
     p->kblks_per_split = ceil_div(p->kblks_total, s);
@@ -711,16 +786,20 @@ template <typename T>
 static int run_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, const TnDst& C,
                   int64_t ldc, float* ws, cudaStream_t st) {
     using TR = TcTraits<T>;
-    const int esize = (int)sizeof(T);
+    constexpr int NP = TR::NP;
     TnPlan p;
     CN_CHECK_ARG(tn_plan(prec, M, N, K, &p), "tcgen05 gemm_tn: unsupported shape M=%d N=%d (need M %% 128 == 0, N %% %d == 0)", M, N, TR::KB);
+    if (NP == 2) {
+        CN_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 255) == 0 && (reinterpret_cast<uintptr_t>(B) & 255) == 0 && lda % 64 == 0 && ldb % 64 == 0,
+                     "tcgen05 gemm_tn: bf16x3 operands need 256-byte aligned bases and row pitches that are multiples of 64");
+    }
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, TR::DT, esize, A, K, M, lda, TR::KB, TR::KB, TR::MN_SWIZZLE);
+    int rc = make_map(&tmA, TR::DT, TR::TMA_ES, A, K, (int64_t)NP * M, NP * lda, TR::KB, TR::TN_KROWS, TR::MN_SWIZZLE);
     if (rc) return rc;
-    rc = make_map(&tmB, TR::DT, esize, B, K, N, ldb, TR::KB, TR::KB, TR::MN_SWIZZLE);
+    rc = make_map(&tmB, TR::DT, TR::TMA_ES, B, K, (int64_t)NP * N, NP * ldb, TR::KB, TR::TN_KROWS, TR::MN_SWIZZLE);
     if (rc) return rc;
-    const int box_bytes = TR::KB * 128;
-    const size_t stage_bytes = (size_t)(TN_MBLK / TR::KB) * box_bytes + (size_t)(p.Nblk / TR::KB) * box_bytes;
+    const int box_bytes = TR::TN_KROWS * 128;
+    const size_t stage_bytes = (size_t)NP * ((size_t)(TN_MBLK / TR::KB) * box_bytes + (size_t)(p.Nblk / TR::KB) * box_bytes);
     const size_t smem = 1024 + TN_STAGES * stage_bytes + sizeof(TnBars) + 64;
     static bool attr_done[64] = {};
     if (int rc_ = ensure_big_smem(tc_tn_kernel<T>, attr_done)) return rc_;
@@ -738,6 +817,7 @@ int gemm_tc_tn(int prec, int M, int N, int64_t K, const void* A, int64_t lda, co
         return 0;
     }
     if (prec == CARTNET_PREC_BF16) return run_tn<__nv_bfloat16>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
+    if (prec == CARTNET_PREC_BF16X3) return run_tn<bf16p_t>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
     return run_tn<tf32_t>(prec, M, N, K, A, lda, B, ldb, C, ldc, ws, st);
 }
 

@@ -19,26 +19,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ G1, const float* _
         const int r = (int)(i / D), c = (int)(i % D), blk = r / D, rr = r % D;
         const float* src = (blk & 1) ? A1 : G1;
         const float v = src[(int64_t)rr * 3 * D + (blk >> 1) * D + c];
-        W1n[i] = from_f32<T>(v);
-        W1nT[(int64_t)c * 4 * D + r] = from_f32<T>(v);
+        store1<T>(&W1n[i], v);
+        store1<T>(&W1nT[(int64_t)c * 4 * D + r], v);
     } else if (i < 6 * DD) {     // W1e[r, c], r in [0,2D): blocks G1_e, A1_e
         const int64_t k = i - 4 * DD;
         const int r = (int)(k / D), c = (int)(k % D), blk = r / D, rr = r % D;
         const float v = (blk ? A1 : G1)[(int64_t)rr * 3 * D + 2 * D + c];
-        W1e[k] = from_f32<T>(v);
-        W1eT[(int64_t)c * 2 * D + r] = from_f32<T>(v);
+        store1<T>(&W1e[k], v);
+        store1<T>(&W1eT[(int64_t)c * 2 * D + r], v);
     } else if (i < 7 * DD) {
         const int64_t k = i - 6 * DD;
         const int r = (int)(k / D), c = (int)(k % D);
         const float v = G2[k];
-        G2t[k] = from_f32<T>(v);
-        G2T[(int64_t)c * D + r] = from_f32<T>(v);
+        store1<T>(&G2t[k], v);
+        store1<T>(&G2T[(int64_t)c * D + r], v);
     } else if (i < 8 * DD) {
         const int64_t k = i - 7 * DD;
         const int r = (int)(k / D), c = (int)(k % D);
         const float v = A2[k];
-        A2t[k] = from_f32<T>(v);
-        A2T[(int64_t)c * D + r] = from_f32<T>(v);
+        store1<T>(&A2t[k], v);
+        store1<T>(&A2T[(int64_t)c * D + r], v);
     }
 }
 
@@ -202,9 +202,16 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     CN_TRY(cartnet_colsum(L->dP, 1, prec, N, D, 4 * D, L->dbg1, L->partial, st));
     CN_TRY(cartnet_colsum(toff((const void*)L->dP, prec, D), 1, prec, N, D, 4 * D, L->dba1, L->partial, st));
     {
-        cartnet_gemm_t d = gemm_desc(prec, N, D, 4 * D, L->dP, 4 * D, L->W1nT_t, 4 * D);
-        d.resid = L->dx_out; d.ldr = D; d.out_f32 = L->dx_in; d.ldo = D;
-        CN_TRY(cartnet_gemm(&d, st));
+        // bf16x3: the resident weight slice (32 x K x 4 B) must fit 128 KB: K = 4D > 1024 is contracted in two halves,
+        // the second one accumulating onto the first through the residual input (same element, same thread)
+        const int ks = (prec == CARTNET_PREC_BF16X3 && D > 256) ? 2 : 1;
+        const int Kh = 4 * D / ks;
+        for (int h = 0; h < ks; ++h) {
+            cartnet_gemm_t d = gemm_desc(prec, N, D, Kh, toff((const void*)L->dP, prec, (int64_t)h * Kh), 4 * D,
+                                         toff((const void*)L->W1nT_t, prec, (int64_t)h * Kh), 4 * D);
+            d.resid = h == 0 ? L->dx_out : L->dx_in; d.ldr = D; d.out_f32 = L->dx_in; d.ldo = D;
+            CN_TRY(cartnet_gemm(&d, st));
+        }
     }
     // d(W_i), d(W_j) = dP^T x, four [D,D] blocks: G1_i, A1_i, G1_j, A1_j
     {

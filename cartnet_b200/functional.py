@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype
+from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype
 
 
 def _round_up(v: int, m: int) -> int:
@@ -27,8 +27,8 @@ def _round_up(v: int, m: int) -> int:
 def _to_t(w: torch.Tensor, prec: int) -> torch.Tensor:
     """weights are tiny (<= 1 MB): a torch cast is plumbing, not hot path"""
     w = w.detach()
-    if prec == PREC_TF32:
-        return ops.cast(w.contiguous(), prec)          # fp32 words rounded to tf32 (the MMA would truncate otherwise)
+    if prec in (PREC_TF32, PREC_BF16X3):
+        return ops.cast(w.contiguous(), prec)          # fp32 words rounded to tf32 (the MMA would truncate otherwise) / hi|lo bf16 pairs
     return w.contiguous() if f32_storage(prec) else w.to(torch.bfloat16).contiguous()
 
 
@@ -37,7 +37,7 @@ class _EdgeEncoderFn(torch.autograd.Function):
     def forward(ctx, cart_dist, cart_dir, means, betas, Wa, ba, Wb, bb, upper, invariant, prec, holder):
         dim_edge = int(Wa.shape[1])
         D2, D = int(Wa.shape[0]), int(Wb.shape[0])
-        KF = _round_up(dim_edge, {PREC_FP32: 4, PREC_BF16: 64, PREC_TF32: 32}[prec])   # tcgen05: whole 128-byte K blocks
+        KF = _round_up(dim_edge, {PREC_FP32: 4, PREC_BF16: 64, PREC_TF32: 32, PREC_BF16X3: 64}[prec])   # tcgen05: whole 128-byte K blocks
         T = t_dtype(prec)
         dev = cart_dist.device
         E = int(cart_dist.shape[0])
@@ -245,7 +245,11 @@ class _LayerFn(torch.autograd.Function):
         # sum_e dZ = sum_n (sum_{e -> n} dZ): N rows instead of E (two D-wide reductions, as in csrc/layer.cu)
         db1 = torch.cat([ops.colsum(dP[:, :D], prec), ops.colsum(dP[:, D:2 * D], prec)])
         dx_in = torch.empty(N, D, dtype=torch.float32, device=dev)
-        ops.gemm(prec, dP, _to_t(W1n.t(), prec), resid=dx_out, out_f32=dx_in)
+        W1nT = _to_t(W1n.t(), prec)
+        ks = 2 if (prec == PREC_BF16X3 and D > 256) else 1      # as in csrc/layer.cu: K = 4D in two halves
+        Kh = 4 * D // ks
+        for h in range(ks):
+            ops.gemm(prec, dP[:, h * Kh:(h + 1) * Kh], W1nT[:, h * Kh:(h + 1) * Kh], resid=dx_out if h == 0 else dx_in, out_f32=dx_in)
         dW1n = ops.gemm_tn(prec, dP, x_t)
         dw1, db1n = sums1[D:2 * D].clone(), sums1[:D].clone()
         dw2, db2n = sums2[D:].clone(), sums2[:D].clone()

@@ -13,13 +13,17 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_FP32, PREC_TF32  # noqa: F401
+from ._lib import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32  # noqa: F401
 
 EPS_BN = 1e-5
 
 
 def t_dtype(prec: int) -> torch.dtype:
-    """storage type of the GEMM operands: bf16 for PREC_BF16, fp32 for PREC_FP32 (SIMT) and PREC_TF32 (tcgen05)"""
+    """torch dtype of the buffers that hold GEMM operands: bf16 for PREC_BF16; 4-byte words for PREC_FP32 (SIMT),
+    PREC_TF32 (tcgen05 kind::tf32) and PREC_BF16X3. In PREC_BF16X3 the words are OPAQUE: each run of 64 elements
+    (256 bytes) holds 64 bf16 high parts followed by 64 bf16 low parts (value = hi + lo, ~16 mantissa bits), the
+    layout the split-precision tcgen05 GEMMs read with TMA (csrc/common.cuh::bf16p_t). Only the library's kernels
+    may interpret such a buffer; column slices must start at multiples of 64."""
     return torch.bfloat16 if prec == PREC_BF16 else torch.float32
 
 
@@ -305,7 +309,7 @@ def colstats(x, running_mean=None, running_var=None, momentum: float = 0.1, shif
     """Per-column mean / biased variance over rows of x (fp32, or T of `prec`); updates running stats in place
     (train-mode BN). `shift` [C]: x was stored centred (x = true - shift); only the running-mean update sees it."""
     lib = _lib.load()
-    is_t = 0 if x.dtype == torch.float32 and prec != PREC_TF32 else 1
+    is_t = 0 if x.dtype == torch.float32 and prec not in (PREC_TF32, PREC_BF16X3) else 1
     _req(x, t_dtype(prec) if is_t else torch.float32, "x")
     rows, Cc = int(x.shape[0]), int(x.shape[1])
     mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
@@ -331,8 +335,9 @@ def gate_center(H_g, G2, bg2, running_mean, training: bool, prec: int):
 
 
 def colsum(x, prec: int) -> torch.Tensor:
+    """column sums of a T-typed tensor of mode `prec` (fp32 words in the fp32 / tf32 modes)"""
     lib = _lib.load()
-    is_t = 0 if x.dtype == torch.float32 else 1
+    is_t = 1 if (x.dtype != torch.float32 or prec == PREC_BF16X3) else 0
     _req(x, torch.float32 if not is_t else t_dtype(prec), "x")
     rows, Cc = int(x.shape[0]), int(x.shape[1])
     out = torch.empty(Cc, dtype=torch.float32, device=x.device)
@@ -472,6 +477,16 @@ def cast(x, prec: int) -> torch.Tensor:
     rows, Cc = int(x.shape[0]), int(x.shape[1])
     y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=x.device)
     _lib.check(lib.cartnet_cast_rows(_p(x), _ld2(x), _p(y), Cc, rows, Cc, prec, _stream()), "cast_rows")
+    return y
+
+
+def uncast(x_t, prec: int) -> torch.Tensor:
+    """T -> fp32 values (exact): the only way to read a bf16x3 buffer outside the library's kernels."""
+    lib = _lib.load()
+    _req(x_t, t_dtype(prec), "x_t")
+    rows, Cc = int(x_t.shape[0]), int(x_t.shape[1])
+    y = torch.empty(rows, Cc, dtype=torch.float32, device=x_t.device)
+    _lib.check(lib.cartnet_uncast_rows(_p(x_t), _ld2(x_t), _p(y), Cc, rows, Cc, prec, _stream()), "uncast_rows")
     return y
 
 

@@ -15,6 +15,12 @@
  *   CARTNET_PREC_FP32 : T = float,         GEMMs on the fp32 SIMT pipe  (1e-5 parity path)
  *   CARTNET_PREC_BF16 : T = __nv_bfloat16, GEMMs on tcgen05/TMEM fed by TMA (2e-3 path)
  *   CARTNET_PREC_TF32 : T = float,         GEMMs on tcgen05 kind::tf32 reading the fp32 tensors directly
+ *   CARTNET_PREC_BF16X3 : T = 4-byte opaque slot; split-precision tensor-core mode. Every run of 64 consecutive elements
+ *                       (256 bytes, 256-byte aligned) stores 64 bf16 high parts followed by 64 bf16 low parts
+ *                       (value = hi + lo, ~16 mantissa bits); GEMMs are three tcgen05 kind::f16 MMAs per product
+ *                       (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM). Bases must be 256-byte aligned, row pitches
+ *                       and column offsets multiples of 64 elements. This is the tensor-core mode that holds the 2e-3
+ *                       tolerance in TRAINING mode (edge BatchNorm amplifies operand rounding ~15x).
  */
 #ifndef CARTNET_B200_H
 #define CARTNET_B200_H
@@ -27,7 +33,7 @@ extern "C" {
 
 typedef void* cartnet_stream_t; /* cudaStream_t */
 
-enum { CARTNET_PREC_FP32 = 0, CARTNET_PREC_BF16 = 1, CARTNET_PREC_TF32 = 2 };
+enum { CARTNET_PREC_FP32 = 0, CARTNET_PREC_BF16 = 1, CARTNET_PREC_TF32 = 2, CARTNET_PREC_BF16X3 = 3 };
 enum { CARTNET_ACT_NONE = 0, CARTNET_ACT_SILU = 1, CARTNET_ACT_MUL_DSILU = 2 };
 
 int cartnet_version(void);
@@ -279,6 +285,10 @@ int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz
 /* dst_t = (T) src  over [rows, C]. */
 int cartnet_cast_rows(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t C,
                       int32_t prec, cartnet_stream_t stream);
+
+/* dst (fp32) = value of src_t over [rows, C]: the inverse view of cartnet_cast_rows (exact; in the bf16x3 mode hi + lo). */
+int cartnet_uncast_rows(const void* src_t, int64_t lds, float* dst, int64_t ldd, int64_t rows, int32_t C,
+                        int32_t prec, cartnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Whole-layer entry points -- CartNet_layer.forward (models/cartnet.py:204-274) and its backward as ONE call

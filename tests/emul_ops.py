@@ -15,7 +15,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_FP32, PREC_TF32, GraphPlan, f32_storage, needs_shadow, t_dtype  # noqa: F401
+from cartnet_b200.ops import ACT_MUL_DSILU, ACT_NONE, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32, GraphPlan, f32_storage, needs_shadow, t_dtype  # noqa: F401
 
 EPS_BN = 1e-5
 
@@ -33,10 +33,23 @@ def _rna_tf32(t):
     return ((i + 0x1000) & ~0x1fff).view(torch.float32)
 
 
+def _pair_bf16(t):
+    """fp32 -> hi + lo with hi = bf16(t), lo = bf16(t - hi): what a bf16x3 operand pair represents (~16 mantissa bits)"""
+    t = t.to(torch.float32)
+    hi = t.to(torch.bfloat16).to(torch.float32)
+    lo = (t - hi).to(torch.bfloat16).to(torch.float32)
+    return hi + lo
+
+
 def _shadow(t, prec):
+    """value -> T-typed storage of precision mode `prec` (the rounding a kernel's store4<T> applies)"""
     if not needs_shadow(prec):
-        return t
-    return _rna_tf32(t) if prec == PREC_TF32 else t.to(t_dtype(prec))
+        return t.to(torch.float32)
+    if prec == PREC_TF32:
+        return _rna_tf32(t.to(torch.float32))
+    if prec == PREC_BF16X3:
+        return _pair_bf16(t)
+    return t.to(t_dtype(prec))
 
 
 def _dsilu(z):
@@ -87,7 +100,7 @@ def edge_features(cart_dist, cart_dir, means, betas, cutoff_upper, invariant, ld
     feat = F.pad(feat, (0, ld - used))
     if ld > used:
         feat[:, used] = 1.0          # ones column: the bias gradient rides in the weight-gradient GEMM
-    return feat.to(t_dtype(prec))
+    return _shadow(feat, prec)
 
 
 def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1=None, z_out=None,
@@ -100,7 +113,7 @@ def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1
     if gather1 is not None:
         v = v + _f(gather1)[gidx1.long()]
     if z_out is not None:
-        z_out.copy_(v.to(z_out.dtype))
+        z_out.copy_(_shadow(v, prec))
     if act == ACT_SILU:
         v = F.silu(v)
     elif act == ACT_MUL_DSILU:
@@ -110,7 +123,7 @@ def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1
     if out_f32 is not None:
         out_f32.copy_(v.to(torch.float32))
     if out_t is not None:
-        out_t.copy_(v.to(out_t.dtype))
+        out_t.copy_(_shadow(v, prec))
 
 
 def gemm_colstats(prec, A, B, bias, out_t, running_mean=None, running_var=None, momentum=0.1, shift=None):
@@ -198,8 +211,7 @@ def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius
     n = gn.shape[0]
     corr = (s1 / n + gn * s2 / n) if training else 0.0
     dg = _f(bn_w) * rstd * (dghat - corr)
-    T = t_dtype(prec)
-    return ds.to(T), dg.to(T), torch.cat([s1, s2, ds.sum(0)]).float()
+    return _shadow(ds, prec), _shadow(dg, prec), torch.cat([s1, s2, ds.sum(0)]).float()
 
 
 def segment_sum(x, ptr, perm, num_nodes, out, prec):
@@ -207,7 +219,8 @@ def segment_sum(x, ptr, perm, num_nodes, out, prec):
     seg = torch.repeat_interleave(torch.arange(num_nodes), counts)
     rows = _f(x) if perm is None else _f(x)[perm.long()]
     res = torch.zeros(num_nodes, x.shape[1], dtype=rows.dtype).index_add_(0, seg, rows)
-    out.copy_(res.to(out.dtype))
+    out_is_t = not (out.dtype == torch.float32 and not f32_storage(prec))
+    out.copy_(_shadow(res, prec) if out_is_t else res.to(out.dtype))
     return out
 
 
@@ -220,7 +233,7 @@ def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes, out, prec):
 
 def dsilu_mul(dy, z, prec, want_colsum=False):
     v = _f(dy) * _dsilu(_f(z))
-    y = _shadow(v.float(), prec) if prec == PREC_TF32 else v.to(t_dtype(prec))
+    y = _shadow(v.float(), prec)
     return (y, v.double().sum(0).float()) if want_colsum else y
 
 
