@@ -132,7 +132,13 @@ class DevicePrefetcher:
             self._next = None
             return
         with torch.cuda.stream(self.stream):
-            b = CrystalBatch(**hb.__dict__).to(self.device, non_blocking=True)
+            # a PyG Batch keeps its fields in a store, not in __dict__: go through keys() / getattr
+            names = list(hb.keys()) if callable(getattr(hb, "keys", None)) else [k for k in hb.__dict__ if not k.startswith("_")]
+            fields = {k: getattr(hb, k) for k in names}
+            for k in ("edges_dst_sorted", "non_H_index"):       # optional hints set as plain attributes
+                if k not in fields and getattr(hb, k, None) is not None:
+                    fields[k] = getattr(hb, k)
+            b = CrystalBatch(**fields).to(self.device, non_blocking=True)
             if hasattr(b, "edge_index"):
                 get_plan(b)                     # cached by edge_index identity; the layers find it ready
             ev = torch.cuda.Event()

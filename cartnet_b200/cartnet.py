@@ -88,7 +88,10 @@ def _mask_index(mask: torch.Tensor) -> torch.Tensor:
 
 
 def _operand(t: torch.Tensor, prec: int):
-    """T-typed copy left on the tensor by the producing kernel, if it is still valid."""
+    """T-typed copy left on the tensor by the producing kernel, if it is still valid. In fp32 mode the fp32 tensor IS
+    the operand (no tag is kept: a tensor that referenced itself would only be freed by the cyclic GC)."""
+    if not ops.needs_shadow(prec):
+        return t if (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) else None
     sh = getattr(t, "_cn_t", None)
     if sh is None or sh[1] != prec or sh[2] != t._version or sh[0].shape != t.shape:
         return None
@@ -96,7 +99,7 @@ def _operand(t: torch.Tensor, prec: int):
 
 
 def _tag(t: torch.Tensor, t_copy, prec: int):
-    if t_copy is not None:
+    if t_copy is not None and t_copy is not t:
         t._cn_t = (t_copy, prec, t._version)
     return t
 
@@ -120,16 +123,22 @@ class _PackW1(torch.autograd.Function):
         return dG1, dA1
 
 
+def _graph_ptr(batch_vec: torch.Tensor, num_graphs: int) -> torch.Tensor:
+    """First node of every crystal, from the (sorted) batch vector itself -- NOT from `natoms`: with the reference's
+    --disable_H the nodes are filtered but data.natoms keeps counting the hydrogens (datasetADP.py:52-72), so
+    cumsum(natoms) would describe ranges that no longer match x. No host synchronisation."""
+    edges = torch.arange(num_graphs + 1, device=batch_vec.device, dtype=batch_vec.dtype)
+    return torch.searchsorted(batch_vec.contiguous(), edges).to(torch.int32)
+
+
 class _BroadcastRows(torch.autograd.Function):
     """rows[B, C] -> rows[batch] ([N, C]) for a SORTED batch vector (nodes are grouped by crystal). Forward is the
     same gather as `t[batch.batch]` (cartnet.py:145); backward is a deterministic segmented sum over each crystal's
     contiguous node range (C-ABI cartnet_segment_sum) instead of torch's sort-based index_put accumulation."""
 
     @staticmethod
-    def forward(ctx, rows, batch_vec, natoms):
-        num_graphs = int(natoms.numel())
-        ptr = torch.zeros(num_graphs + 1, dtype=torch.int32, device=rows.device)
-        ptr[1:] = torch.cumsum(natoms.to(rows.device), 0).to(torch.int32)      # no host sync (bincount would need one)
+    def forward(ctx, rows, batch_vec, num_graphs):
+        ptr = _graph_ptr(batch_vec, num_graphs)
         ctx.save_for_backward(ptr)
         ctx.num_graphs = num_graphs
         return rows.index_select(0, batch_vec)
@@ -149,7 +158,7 @@ def _per_graph_rows(rows, batch):
     nat = getattr(batch, "natoms", None)
     c = int(rows.shape[1])
     if rows.is_cuda and nat is not None and int(nat.numel()) == int(rows.shape[0]) and c % 4 == 0 and c // 4 <= 256 and 256 % (c // 4) == 0:
-        return _BroadcastRows.apply(rows, batch.batch, nat)
+        return _BroadcastRows.apply(rows, batch.batch, int(nat.numel()))      # natoms only tells HOW MANY crystals there are
     return rows[batch.batch]
 
 
@@ -331,12 +340,9 @@ class _SegmentMean(torch.autograd.Function):
     contiguous node range (C-ABI cartnet_segment_sum) instead of torch_scatter's atomic scatter (cartnet.py:326)."""
 
     @staticmethod
-    def forward(ctx, rows, batch_vec, natoms):
-        num_graphs = int(natoms.numel())
-        nat = natoms.to(rows.device)
-        ptr = torch.zeros(num_graphs + 1, dtype=torch.int32, device=rows.device)
-        ptr[1:] = torch.cumsum(nat, 0).to(torch.int32)
-        inv = 1.0 / nat.clamp(min=1).to(torch.float32).unsqueeze(-1)
+    def forward(ctx, rows, batch_vec, num_graphs):
+        ptr = _graph_ptr(batch_vec, num_graphs)      # node counts as they are in x, not the (possibly stale) natoms field
+        inv = 1.0 / (ptr[1:] - ptr[:-1]).clamp(min=1).to(torch.float32).unsqueeze(-1)
         out = torch.empty(num_graphs, rows.shape[1], dtype=torch.float32, device=rows.device)
         ops.segment_sum(rows.detach().contiguous(), ptr, None, num_graphs, out, PREC_FP32)
         ctx.save_for_backward(batch_vec, inv)
@@ -364,7 +370,7 @@ class Scalar_head(nn.Module, _PrecisionMixin):
         c = self.MLP[0].out_features
         if natoms is not None and c % 4 == 0 and c // 4 <= 256 and 256 % (c // 4) == 0:
             h = CF.linear_silu(batch.x, self.MLP[0].weight, self.MLP[0].bias, self.prec)
-            pooled = _SegmentMean.apply(h, batch.batch, natoms)
+            pooled = _SegmentMean.apply(h, batch.batch, int(natoms.numel()))
             batch.x = F.linear(pooled, self.MLP[2].weight, self.MLP[2].bias).squeeze(-1)
             return batch.x, batch.y
         dim_size = int(batch.batch.max().item() + 1)

@@ -352,6 +352,9 @@ class _NativeLayerFn(torch.autograd.Function):
         import ctypes as C
         from . import _lib
         lib = _lib.load()
+        if ctx.keep is None:
+            raise RuntimeError("cartnet_b200: CartNet_layer backward was called a second time, but its saved activations "
+                               "have already been freed (run the forward pass again; retain_graph is not supported)")
         L = ctx.L
         N, E, D, prec = ctx.dims
         T = t_dtype(prec)

@@ -72,8 +72,9 @@ _scratch = {}
 
 
 def _partial(device, nbytes: int) -> torch.Tensor:
-    """fp64 scratch for the fixed-order column reductions (stream-ordered reuse)."""
-    key = (device, "partial")
+    """fp64 scratch for the fixed-order column reductions (stream-ordered reuse: one buffer per device AND stream, so
+    that work issued on a side stream never shares scratch with the main stream)."""
+    key = (device, _stream(), "partial")
     buf = _scratch.get(key)
     if buf is None or buf.numel() * 8 < nbytes:
         buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
@@ -82,7 +83,7 @@ def _partial(device, nbytes: int) -> torch.Tensor:
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    key = (device, "ws")
+    key = (device, _stream(), "ws")
     buf = _scratch.get(key)
     if buf is None or buf.numel() * 4 < nbytes:
         buf = torch.empty((nbytes + 3) // 4 + 64, dtype=torch.float32, device=device)

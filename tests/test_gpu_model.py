@@ -75,18 +75,24 @@ def test_fp32_layer_matches_reference_layer(name, training):
                 assert common.rel_err(lg.norm2.running_mean, lo.norm2.running_mean) < 1e-5
 
 
-@pytest.mark.parametrize("precision,tol_eval,tol_train", [("bf16", 2e-3, 6e-2), ("tf32", 2e-3, 1e-2)])
-def test_tensor_core_path(golden_model, precision, tol_eval, tol_train):
-    """north_star: tensor-core path within 2e-3 relative (eval mode = the mode validation MAE is computed in).
-    Training mode: BatchNorm over batch statistics amplifies operand rounding ~15x on random weights -- the
-    budget asserted is the one the CPU emulation of the same rounding shows (tests/test_host_logic.py)."""
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32", "bf16"])
+def test_tensor_core_path(golden_model, precision):
+    """north_star: tensor-core path within 2e-3 relative, validation MAE identical to 3 significant digits.
+    bf16x3 (the default tensor-core mode, what bench.py times) is held to 2e-3 in TRAINING mode as well -- prediction and
+    every gradient (tests/test_gpu_bf16x3.py runs the same check on all three golden cases). The single-rounding modes
+    (tf32, bf16) are eval-mode modes: under batch statistics the edge BatchNorm amplifies their operand rounding ~15x
+    (measured 5e-3 / 3e-2 on this case), which is why neither is the default; their training-mode numbers are only
+    bounded loosely here as a regression guard and are NOT a parity claim."""
     name = "adp"
     shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
     batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
     res = common.run_train_step(_model(kw, seed, lrad, precision), batch0)
     gm = golden_model
-    assert common.rel_err(res["pred_eval"], torch.from_numpy(gm[name + "/pred_eval"])) < tol_eval
-    assert common.rel_err(res["pred"], torch.from_numpy(gm[name + "/pred"])) < tol_train
+    assert common.rel_err(res["pred_eval"], torch.from_numpy(gm[name + "/pred_eval"])) < 2e-3
+    if precision == "bf16x3":
+        common.check_against_golden(res, gm, name, tol=2e-3, gtol=2e-3)
+    else:
+        assert common.rel_err(res["pred"], torch.from_numpy(gm[name + "/pred"])) < {"tf32": 1e-2, "bf16": 6e-2}[precision]   # regression guard only
     mae_ref = float(np.abs(gm[name + "/pred_eval"] - batch0.y.cpu().numpy()).mean())
     mae = float((res["pred_eval"] - batch0.y).abs().mean())
     assert abs(mae - mae_ref) / mae_ref < 5e-4                 # validation MAE identical to 3 significant digits
@@ -106,7 +112,7 @@ def test_larger_batch_against_oracle_and_determinism(precision):
     model.load_state_dict(sd)
     model.cuda()
     got = common.run_train_step(model, batch_cpu.clone().to("cuda"))
-    tol = 1e-5 if precision == "fp32" else 6e-2
+    tol = 1e-5 if precision == "fp32" else 6e-2       # bf16: regression guard only (training-mode parity is bf16x3's, tests/test_gpu_bf16x3.py)
     assert common.rel_err(got["pred"], ref["pred"]) < tol
     assert common.rel_err(got["pred_eval"], ref["pred_eval"]) < (1e-5 if precision == "fp32" else 2e-3)
     if precision == "fp32":
@@ -297,6 +303,7 @@ def test_other_hidden_widths(dim_in, layers):
     sd = fixtures.make_state_dict(orc.state_dict(), seed)
     orc.load_state_dict(sd)
     ref = common.run_train_step(orc, batch_cpu)
+    # bf16 row: regression guard, not a parity claim (the tensor-core parity mode is bf16x3, tests/test_gpu_bf16x3.py)
     for precision, tol_train, tol_eval in (("fp32", 2e-5, 1e-5), ("bf16", 1e-1, 5e-3)):
         model = cartnet_b200.CartNet(dim_in, 64, layers, precision=precision, **kw)
         model.load_state_dict(sd)
