@@ -58,8 +58,21 @@ def _fill_cfg(cfg, monkeypatch):
     monkeypatch.setattr(cfg, "dataset", SimpleNamespace(name="ADP"), raising=False)
 
 
-def test_reference_call_sites_run_unchanged_on_the_replacement(monkeypatch, tmp_path):
-    ref_cartnet, _, _, cfg = ref_loader.load()
+@pytest.fixture
+def reference_modules():
+    """Imports the reference through the shim and removes every trace afterwards: once `torch_geometric.graphgym.config`
+    is importable, cartnet_b200 reads the GLOBAL cfg.radius / cfg.invariant like the reference does (cartnet.py:156,201),
+    which must not leak into the other tests of this process."""
+    before_mods, before_path = set(sys.modules), list(sys.path)
+    yield ref_loader.load()
+    for name in set(sys.modules) - before_mods:
+        if name.split(".")[0] in ("torch_geometric", "torch_scatter", "models", "train", "dataset", "wandb"):
+            del sys.modules[name]
+    sys.path[:] = before_path
+
+
+def test_reference_call_sites_run_unchanged_on_the_replacement(monkeypatch, tmp_path, reference_modules):
+    ref_cartnet, _, _, cfg = reference_modules
     _fill_cfg(cfg, monkeypatch)
     monkeypatch.setattr(torch.nn.Module, "to", lambda self, *a, **k: self)      # `.to("cuda:0")` (master.py:33) without a GPU
     master = importlib.import_module("models.master")
