@@ -60,6 +60,10 @@ SIGNATURES = {
     "cartnet_nlist_count": (i32, [vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, vp]),
     "cartnet_exclusive_scan_i32": (i32, [vp, i32, vp, vp]),
     "cartnet_nlist_fill": (i32, [vp, vp, vp, vp, i32, f32, f32, vp, i32, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cartnet_nlist_cells_workspace": (i64, [i32, i32]),
+    "cartnet_nlist_cells_build": (i32, [vp, vp, vp, vp, i32, i32, f32, vp, i32, vp, vp]),
+    "cartnet_nlist_cells_count": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, i32, vp, vp, vp]),
+    "cartnet_nlist_cells_fill": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cartnet_nlist_knn_mask": (i32, [vp, vp, i32, i32, f32, i32, vp, vp, vp, vp]),
     "cartnet_graph_split": (i32, [vp, i64, i32, vp, vp, vp, vp]),
     "cartnet_graph_csr": (i32, [vp, i64, i32, vp, vp, vp, vp]),

@@ -73,29 +73,46 @@ __device__ __forceinline__ float exact_d2(const CellGeom& g, const float p1[3], 
     return __fadd_rn(__fadd_rn(sq[0], sq[1]), sq[2]);  // utils.py:197
 }
 
+struct NlistOut {
+    int64_t* edge_index; int64_t num_edges;
+    float *unit_cell, *dist, *direction, *cart_dist, *cart_dir;
+    int32_t *src32, *dst32;
+};
+
+// one accepted (pair, image): every output field of edge w (utils.py:206-213,235-237; figshare_dataset.py:67-68)
+__device__ __forceinline__ void write_edge(const NlistOut& o, int64_t w, int i1, int i2, int u1, int u2, int u3, float d2,
+                                           const float delta[3]) {
+    o.edge_index[w] = (int64_t)i2;                 // row 0: source j   (utils.py:235)
+    o.edge_index[o.num_edges + w] = (int64_t)i1;   // row 1: destination i
+    o.unit_cell[3 * w + 0] = (float)u1;
+    o.unit_cell[3 * w + 1] = (float)u2;
+    o.unit_cell[3 * w + 2] = (float)u3;
+    const float dd = __fsqrt_rn(d2);
+    o.dist[w] = dd;
+    o.direction[3 * w + 0] = delta[0];
+    o.direction[3 * w + 1] = delta[1];
+    o.direction[3 * w + 2] = delta[2];
+    if (o.cart_dist) o.cart_dist[w] = dd;            // figshare_dataset.py:67
+    if (o.cart_dir) {                                // figshare_dataset.py:68
+        const float nrm = fmaxf(dd, 1e-12f);
+        o.cart_dir[3 * w + 0] = __fdiv_rn(delta[0], nrm);
+        o.cart_dir[3 * w + 1] = __fdiv_rn(delta[1], nrm);
+        o.cart_dir[3 * w + 2] = __fdiv_rn(delta[2], nrm);
+    }
+    if (o.src32) o.src32[w] = i2;
+    if (o.dst32) o.dst32[w] = i1;
+}
+
+// All-pairs scan of one destination row by one warp (small crystals): returns the row's edge count.
 template <bool FILL>
-__global__ void __launch_bounds__(128)
-nlist_kernel(const float* __restrict__ pos, const float* __restrict__ cell, const int32_t* __restrict__ crystal_ptr,
-             const int32_t* __restrict__ node_crystal, int num_nodes, float radius, float radius_sq,
-             const int32_t* __restrict__ reps, int reps_stride, int32_t* __restrict__ row_count,
-             const int32_t* __restrict__ row_ptr, int64_t* __restrict__ edge_index, int64_t num_edges,
-             float* __restrict__ unit_cell, float* __restrict__ dist, float* __restrict__ direction,
-             float* __restrict__ cart_dist, float* __restrict__ cart_dir, int32_t* __restrict__ src32,
-             int32_t* __restrict__ dst32) {
-    const int lane = threadIdx.x & 31;
-    const int i1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i1 >= num_nodes) return;
-    const int b = node_crystal[i1];
-    const int a0 = crystal_ptr[b], a1 = crystal_ptr[b + 1];
-    CellGeom g;
-    load_geom(g, cell, reps, reps_stride, b, radius);
+__device__ __forceinline__ int scan_all_pairs(const CellGeom& g, const float* __restrict__ pos, int i1, int a0, int a1, int lane,
+                                              float radius_sq, int64_t out_base, const NlistOut& o) {
     const float p1[3] = {pos[3 * (int64_t)i1], pos[3 * (int64_t)i1 + 1], pos[3 * (int64_t)i1 + 2]};
     const double f1[3] = {
         (double)p1[0] * g.inv[0] + (double)p1[1] * g.inv[3] + (double)p1[2] * g.inv[6],
         (double)p1[0] * g.inv[1] + (double)p1[1] * g.inv[4] + (double)p1[2] * g.inv[7],
         (double)p1[0] * g.inv[2] + (double)p1[1] * g.inv[5] + (double)p1[2] * g.inv[8]};
 
-    int64_t out_base = FILL ? (int64_t)row_ptr[i1] : 0;
     int total = 0;
     for (int chunk = a0; chunk < a1; chunk += 32) {
         const int i2 = chunk + lane;
@@ -126,9 +143,9 @@ nlist_kernel(const float* __restrict__ pos, const float* __restrict__ cell, cons
         // exclusive prefix over lanes -> position of this source's first edge inside the row
         int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o2);
+            if (lane >= o2) incl += v;
         }
         const int chunk_total = __shfl_sync(0xffffffffu, incl, 31);
         if (FILL && cnt > 0) {
@@ -138,32 +155,220 @@ nlist_kernel(const float* __restrict__ pos, const float* __restrict__ cell, cons
                     for (int u3 = lo[2]; u3 <= hi[2]; ++u3) {
                         float d2 = exact_d2(g, p1, p2, u1, u2, u3, delta);
                         if (d2 <= radius_sq && d2 > 0.0001f) {
-                            edge_index[w] = (int64_t)i2;                 // row 0: source j   (utils.py:235)
-                            edge_index[num_edges + w] = (int64_t)i1;     // row 1: destination i
-                            unit_cell[3 * w + 0] = (float)u1;
-                            unit_cell[3 * w + 1] = (float)u2;
-                            unit_cell[3 * w + 2] = (float)u3;
-                            const float dd = __fsqrt_rn(d2);
-                            dist[w] = dd;
-                            direction[3 * w + 0] = delta[0];
-                            direction[3 * w + 1] = delta[1];
-                            direction[3 * w + 2] = delta[2];
-                            if (cart_dist) cart_dist[w] = dd;            // figshare_dataset.py:67
-                            if (cart_dir) {                              // figshare_dataset.py:68
-                                const float nrm = fmaxf(dd, 1e-12f);
-                                cart_dir[3 * w + 0] = __fdiv_rn(delta[0], nrm);
-                                cart_dir[3 * w + 1] = __fdiv_rn(delta[1], nrm);
-                                cart_dir[3 * w + 2] = __fdiv_rn(delta[2], nrm);
-                            }
-                            if (src32) src32[w] = i2;
-                            if (dst32) dst32[w] = i1;
+                            write_edge(o, w, i1, i2, u1, u2, u3, d2, delta);
                             ++w;
                         }
                     }
         }
         total += chunk_total;
     }
+    return total;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+nlist_kernel(const float* __restrict__ pos, const float* __restrict__ cell, const int32_t* __restrict__ crystal_ptr,
+             const int32_t* __restrict__ node_crystal, int num_nodes, float radius, float radius_sq,
+             const int32_t* __restrict__ reps, int reps_stride, int32_t* __restrict__ row_count,
+             const int32_t* __restrict__ row_ptr, NlistOut o) {
+    const int lane = threadIdx.x & 31;
+    const int i1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i1 >= num_nodes) return;
+    const int b = node_crystal[i1];
+    CellGeom g;
+    load_geom(g, cell, reps, reps_stride, b, radius);
+    const int total = scan_all_pairs<FILL>(g, pos, i1, crystal_ptr[b], crystal_ptr[b + 1], lane, radius_sq,
+                                           FILL ? (int64_t)row_ptr[i1] : 0, o);
     if (!FILL && lane == 0) row_count[i1] = total;
+}
+
+// ------------------------------------------------------------------------------------------ cell list
+// Large crystals: atoms are binned on a grid in (wrapped) fractional coordinates whose bins are at least rho_k wide
+// (rho_k = the conservative image half-range of load_geom), so every (source, image) within the radius of a destination
+// sits in one of the 27 bins around the destination's bin. A warp visits those bins, runs the reference's exact fp32 test
+// on every candidate, and restores the reference's row order -- (source index, cell index) ascending, the flat
+// (index2, cell) enumeration of utils.py:116-123,166-170 -- by a rank sort of the accepted keys in shared memory.
+// Crystals that are too small for a useful grid (fewer than kMinBins bins) and rows longer than kRowCap keep the all-pairs scan.
+constexpr int kMinBins = 64;
+constexpr int kRowCap = 1024;
+
+struct CrystalGrid {      // per crystal, in the workspace
+    int32_t nb[3];        // bins per axis (0 = all-pairs path)
+    int32_t bin0;         // first bin of this crystal in the global bin arrays
+};
+
+__global__ void grid_setup_kernel(const float* __restrict__ cell, const int32_t* __restrict__ crystal_ptr, int num_crystals,
+                                  float radius, const int32_t* __restrict__ reps, int reps_stride, CrystalGrid* __restrict__ grids) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_crystals) return;
+    CellGeom g;
+    load_geom(g, cell, reps, reps_stride, b, radius);
+    const int n = crystal_ptr[b + 1] - crystal_ptr[b];
+    int nb[3];
+    double tot = 1.0;
+    for (int k = 0; k < 3; ++k) {
+        nb[k] = g.rho[k] > 0.0 ? (int)floor(1.0 / g.rho[k]) : 1;      // bin width 1/nb >= rho
+        if (nb[k] > 1024) nb[k] = 1024;
+        tot *= (double)(nb[k] > 0 ? nb[k] : 0);
+    }
+    // never more bins than atoms (the bin arrays are sized by the atom count): coarser bins are always valid
+    if (tot > (double)n && tot > 0.0) {
+        const double sc = cbrt((double)n / tot);
+        for (int k = 0; k < 3; ++k) { nb[k] = (int)floor(nb[k] * sc); if (nb[k] < 1) nb[k] = 1; }
+    }
+    const int64_t ncells = (int64_t)(2 * g.rep[0] + 1) * (2 * g.rep[1] + 1) * (2 * g.rep[2] + 1);
+    const bool use = nb[0] >= 1 && nb[1] >= 1 && nb[2] >= 1 && (int64_t)nb[0] * nb[1] * nb[2] >= kMinBins && (int64_t)nb[0] * nb[1] * nb[2] <= n &&
+                     ncells <= 1024 && n < (1 << 22);          // row keys pack (source, cell) into 22 + 10 bits
+    grids[b].nb[0] = use ? nb[0] : 0; grids[b].nb[1] = use ? nb[1] : 0; grids[b].nb[2] = use ? nb[2] : 0;
+    grids[b].bin0 = crystal_ptr[b];          // bins of crystal b live at [crystal_ptr[b], crystal_ptr[b] + nb0*nb1*nb2) (<= its atom count)
+}
+
+// wrapped fractional coordinate, its bin and the integer shift that was removed (f = fw + shift)
+__device__ __forceinline__ void frac_bin(const CellGeom& g, const float p[3], const int32_t nb[3], int bin[3], int shift[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double f = (double)p[0] * g.inv[k] + (double)p[1] * g.inv[3 + k] + (double)p[2] * g.inv[6 + k];
+        const double fl = floor(f);
+        shift[k] = (int)fl;
+        int bk = (int)((f - fl) * (double)nb[k]);
+        bin[k] = bk >= nb[k] ? nb[k] - 1 : (bk < 0 ? 0 : bk);
+    }
+}
+
+// pass 0: bin id + shift of every atom, bin histogram
+__global__ void bin_atoms_kernel(const float* __restrict__ pos, const float* __restrict__ cell, const int32_t* __restrict__ node_crystal,
+                                 int num_nodes, float radius, const int32_t* __restrict__ reps, int reps_stride,
+                                 const CrystalGrid* __restrict__ grids, int32_t* __restrict__ atom_bin, int32_t* __restrict__ bin_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_nodes) return;
+    const int b = node_crystal[i];
+    const CrystalGrid gr = grids[b];
+    if (gr.nb[0] == 0) { atom_bin[i] = -1; return; }
+    CellGeom g;
+    load_geom(g, cell, reps, reps_stride, b, radius);
+    const float p[3] = {pos[3 * (int64_t)i], pos[3 * (int64_t)i + 1], pos[3 * (int64_t)i + 2]};
+    int bin[3], shift[3];
+    frac_bin(g, p, gr.nb, bin, shift);
+    const int id = gr.bin0 + (bin[0] * gr.nb[1] + bin[1]) * gr.nb[2] + bin[2];
+    atom_bin[i] = id;
+    atomicAdd(&bin_count[id], 1);            // integer atomics: order-independent result
+}
+
+__global__ void bin_place_kernel(const int32_t* __restrict__ atom_bin, int num_nodes, const int32_t* __restrict__ bin_ptr,
+                                 int32_t* __restrict__ cursor, int32_t* __restrict__ bin_atoms) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_nodes) return;
+    const int id = atom_bin[i];
+    if (id < 0) return;
+    bin_atoms[bin_ptr[id] + atomicAdd(&cursor[id], 1)] = i;      // order inside a bin is irrelevant: rows are sorted by key afterwards
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+nlist_cells_kernel(const float* __restrict__ pos, const float* __restrict__ cell, const int32_t* __restrict__ crystal_ptr,
+                   const int32_t* __restrict__ node_crystal, int num_nodes, float radius, float radius_sq,
+                   const int32_t* __restrict__ reps, int reps_stride, const CrystalGrid* __restrict__ grids,
+                   const int32_t* __restrict__ bin_ptr, const int32_t* __restrict__ bin_atoms,
+                   int32_t* __restrict__ row_count, const int32_t* __restrict__ row_ptr, NlistOut o) {
+    __shared__ uint32_t keys_sm[FILL ? 4 * kRowCap : 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i1 = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (i1 >= num_nodes) return;
+    const int b = node_crystal[i1];
+    const int a0 = crystal_ptr[b], a1 = crystal_ptr[b + 1];
+    CellGeom g;
+    load_geom(g, cell, reps, reps_stride, b, radius);
+    const CrystalGrid gr = grids[b];
+    const int64_t out_base = FILL ? (int64_t)row_ptr[i1] : 0;
+    const int row_len = FILL ? row_ptr[i1 + 1] - row_ptr[i1] : 0;
+    if (gr.nb[0] == 0 || (FILL && row_len > kRowCap)) {
+        const int total = scan_all_pairs<FILL>(g, pos, i1, a0, a1, lane, radius_sq, out_base, o);
+        if (!FILL && lane == 0) row_count[i1] = total;
+        return;
+    }
+    const float p1[3] = {pos[3 * (int64_t)i1], pos[3 * (int64_t)i1 + 1], pos[3 * (int64_t)i1 + 2]};
+    int bin1[3], s1[3];
+    frac_bin(g, p1, gr.nb, bin1, s1);
+    const int ncell23 = (2 * g.rep[1] + 1) * (2 * g.rep[2] + 1), ncell3 = 2 * g.rep[2] + 1;
+    uint32_t* keys = keys_sm + (FILL ? wib * kRowCap : 0);
+    int total = 0;
+    // 27 neighbour bins in the periodically extended grid: extended coordinate c = bin1 + d -> bin c mod nb, image v = floor(c / nb)
+    for (int nbr = 0; nbr < 27; ++nbr) {
+        int bb[3], v[3];
+        const int d[3] = {nbr / 9 - 1, (nbr / 3) % 3 - 1, nbr % 3 - 1};
+        // (fewer than 3 bins on an axis: the three extended coordinates still differ in v, nothing is visited twice)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = bin1[k] + d[k];
+            v[k] = c < 0 ? -1 : (c >= gr.nb[k] ? 1 : 0);
+            bb[k] = c - v[k] * gr.nb[k];
+        }
+        const int id = gr.bin0 + (bb[0] * gr.nb[1] + bb[1]) * gr.nb[2] + bb[2];
+        const int q0 = bin_ptr[id], q1 = bin_ptr[id + 1];
+        for (int q = q0 + lane; q < q1 + ((32 - ((q1 - q0) & 31)) & 31); q += 32) {       // whole warp iterates together (ballots below)
+            bool ok = false;
+            int i2 = 0, u[3] = {0, 0, 0};
+            float d2 = 0.f, delta[3];
+            if (q < q1) {
+                i2 = bin_atoms[q];
+                const float p2[3] = {pos[3 * (int64_t)i2], pos[3 * (int64_t)i2 + 1], pos[3 * (int64_t)i2 + 2]};
+                int bin2[3], s2[3];
+                frac_bin(g, p2, gr.nb, bin2, s2);
+                // separation f1 - (f2 + u) = f1w - f2w - v  with  v = u + s2 - s1   =>   u = v - s2 + s1
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    u[k] = v[k] - s2[k] + s1[k];
+                    ok = ok && u[k] >= -g.rep[k] && u[k] <= g.rep[k];      // the reference searches +-rep only (utils.py:166-170)
+                }
+                if (ok) {
+                    d2 = exact_d2(g, p1, p2, u[0], u[1], u[2], delta);
+                    ok = d2 <= radius_sq && d2 > 0.0001f;                  // utils.py:202-205
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (FILL && ok) {
+                const int slot = total + __popc(m & ((1u << lane) - 1u));
+                const uint32_t ci = (uint32_t)((u[0] + g.rep[0]) * ncell23 + (u[1] + g.rep[1]) * ncell3 + (u[2] + g.rep[2]));
+                keys[slot] = ((uint32_t)(i2 - a0) << 10) | ci;             // (source, cell) key: needs atoms < 2^22 per crystal, cells < 1024
+            }
+            total += __popc(m);
+        }
+    }
+    if (!FILL) {
+        if (lane == 0) row_count[i1] = total;
+        return;
+    }
+    __syncwarp();
+    // rank sort of the row's keys (unique), then every lane writes the edges of its sorted positions
+    uint32_t mine[kRowCap / 32];
+    int rank[kRowCap / 32];
+    const int per = (total + 31) / 32;
+    for (int t = 0; t < per; ++t) {
+        const int j = lane + 32 * t;
+        mine[t] = j < total ? keys[j] : 0xffffffffu;
+        rank[t] = 0;
+    }
+    for (int i = 0; i < total; ++i) {
+        const uint32_t kv = keys[i];
+        for (int t = 0; t < per; ++t) rank[t] += (kv < mine[t]) ? 1 : 0;
+    }
+    __syncwarp();
+    for (int t = 0; t < per; ++t)
+        if (lane + 32 * t < total) keys[rank[t]] = mine[t];
+    __syncwarp();
+    for (int w = lane; w < total; w += 32) {
+        const uint32_t kv = keys[w];
+        const int i2 = a0 + (int)(kv >> 10);
+        int ci = (int)(kv & 1023u);
+        const int u1 = ci / ncell23 - g.rep[0];
+        ci %= ncell23;
+        const int u2 = ci / ncell3 - g.rep[1], u3 = ci % ncell3 - g.rep[2];
+        const float p2[3] = {pos[3 * (int64_t)i2], pos[3 * (int64_t)i2 + 1], pos[3 * (int64_t)i2 + 2]};
+        float delta[3];
+        const float d2 = exact_d2(g, p1, p2, u1, u2, u3, delta);
+        write_edge(o, out_base + w, i1, i2, u1, u2, u3, d2, delta);
+    }
 }
 
 __global__ void reps_kernel(const float* __restrict__ cell, int num_crystals, float radius, int pbc_mask,
@@ -369,9 +574,9 @@ int cartnet_nlist_count(const float* pos, const float* cell, const int32_t* crys
     CN_CHECK_ARG(pos && cell && crystal_ptr && node_crystal && reps && row_count, "nlist_count: null pointer");
     CN_CHECK_ARG(reps_stride == 0 || reps_stride == 3, "nlist_count: reps_stride must be 0 or 3");
     if (num_nodes <= 0) return 0;
+    NlistOut o = {};
     nlist_kernel<false><<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(
-        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, row_count, nullptr,
-        nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, row_count, nullptr, o);
     CN_LAUNCH_CHECK();
     return 0;
 }
@@ -392,9 +597,84 @@ int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* cryst
     CN_CHECK_ARG(reps_stride == 0 || reps_stride == 3, "nlist_fill: reps_stride must be 0 or 3");
     if (num_nodes <= 0 || num_edges <= 0) return 0;
     CN_CHECK_ARG(edge_index && unit_cell && dist && direction, "nlist_fill: null output");
+    NlistOut o = {edge_index, num_edges, unit_cell, dist, direction, cart_dist, cart_dir, src32, dst32};
     nlist_kernel<true><<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(
-        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, nullptr, row_ptr,
-        edge_index, num_edges, unit_cell, dist, direction, cart_dist, cart_dir, src32, dst32);
+        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, nullptr, row_ptr, o);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+// workspace layout (int32 words): grids [4 B] | atom_bin [N] | bin_count / cursor [N + 1] | bin_ptr [N + 2] | bin_atoms [N]
+static inline int64_t cells_ws_words(int64_t N, int64_t B) { return 4 * B + N + (N + 1) + (N + 2) + N + 16; }
+
+int64_t cartnet_nlist_cells_workspace(int32_t num_nodes, int32_t num_crystals) {
+    return cells_ws_words(num_nodes, num_crystals) * (int64_t)sizeof(int32_t);
+}
+
+struct CellsWs {
+    CrystalGrid* grids;
+    int32_t *atom_bin, *bin_count, *bin_ptr, *bin_atoms;
+};
+static inline CellsWs cells_ws(void* ws, int64_t N, int64_t B) {
+    int32_t* w = (int32_t*)ws;
+    CellsWs c;
+    c.grids = (CrystalGrid*)w; w += 4 * B;
+    c.atom_bin = w; w += N;
+    c.bin_count = w; w += N + 1;
+    c.bin_ptr = w; w += N + 2;
+    c.bin_atoms = w;
+    return c;
+}
+
+int cartnet_nlist_cells_build(const float* pos, const float* cell, const int32_t* crystal_ptr, const int32_t* node_crystal,
+                              int32_t num_nodes, int32_t num_crystals, float radius, const int32_t* reps, int32_t reps_stride,
+                              void* workspace, cartnet_stream_t stream) {
+    CN_CHECK_ARG(pos && cell && crystal_ptr && node_crystal && reps && workspace, "nlist_cells_build: null pointer");
+    CN_CHECK_ARG(reps_stride == 0 || reps_stride == 3, "nlist_cells_build: reps_stride must be 0 or 3");
+    if (num_nodes <= 0 || num_crystals <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const CellsWs c = cells_ws(workspace, num_nodes, num_crystals);
+    grid_setup_kernel<<<ceil_div(num_crystals, 128), 128, 0, st>>>(cell, crystal_ptr, num_crystals, radius, reps, reps_stride, c.grids);
+    CN_LAUNCH_CHECK();
+    CN_CUDA(cudaMemsetAsync(c.bin_count, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
+    bin_atoms_kernel<<<ceil_div(num_nodes, 256), 256, 0, st>>>(pos, cell, node_crystal, num_nodes, radius, reps, reps_stride, c.grids,
+                                                              c.atom_bin, c.bin_count);
+    CN_LAUNCH_CHECK();
+    scan_kernel<<<1, 1024, 0, st>>>(c.bin_count, num_nodes + 1, c.bin_ptr);
+    CN_LAUNCH_CHECK();
+    CN_CUDA(cudaMemsetAsync(c.bin_count, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
+    bin_place_kernel<<<ceil_div(num_nodes, 256), 256, 0, st>>>(c.atom_bin, num_nodes, c.bin_ptr, c.bin_count, c.bin_atoms);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_nlist_cells_count(const float* pos, const float* cell, const int32_t* crystal_ptr, const int32_t* node_crystal,
+                              int32_t num_nodes, int32_t num_crystals, float radius, float radius_sq, const int32_t* reps,
+                              int32_t reps_stride, const void* workspace, int32_t* row_count, cartnet_stream_t stream) {
+    CN_CHECK_ARG(pos && cell && crystal_ptr && node_crystal && reps && workspace && row_count, "nlist_cells_count: null pointer");
+    if (num_nodes <= 0) return 0;
+    const CellsWs c = cells_ws(const_cast<void*>(workspace), num_nodes, num_crystals);
+    NlistOut o = {};
+    nlist_cells_kernel<false><<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(
+        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, c.grids, c.bin_ptr, c.bin_atoms,
+        row_count, nullptr, o);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_nlist_cells_fill(const float* pos, const float* cell, const int32_t* crystal_ptr, const int32_t* node_crystal,
+                             int32_t num_nodes, int32_t num_crystals, float radius, float radius_sq, const int32_t* reps,
+                             int32_t reps_stride, const void* workspace, const int32_t* row_ptr, int64_t* edge_index,
+                             int64_t num_edges, float* unit_cell, float* dist, float* direction, float* cart_dist,
+                             float* cart_dir, int32_t* src32, int32_t* dst32, cartnet_stream_t stream) {
+    CN_CHECK_ARG(pos && cell && crystal_ptr && node_crystal && reps && workspace && row_ptr, "nlist_cells_fill: null pointer");
+    if (num_nodes <= 0 || num_edges <= 0) return 0;
+    CN_CHECK_ARG(edge_index && unit_cell && dist && direction, "nlist_cells_fill: null output");
+    const CellsWs c = cells_ws(const_cast<void*>(workspace), num_nodes, num_crystals);
+    NlistOut o = {edge_index, num_edges, unit_cell, dist, direction, cart_dist, cart_dir, src32, dst32};
+    nlist_cells_kernel<true><<<ceil_div(num_nodes, 4), 128, 0, (cudaStream_t)stream>>>(
+        pos, cell, crystal_ptr, node_crystal, num_nodes, radius, radius_sq, reps, reps_stride, c.grids, c.bin_ptr, c.bin_atoms,
+        nullptr, row_ptr, o);
     CN_LAUNCH_CHECK();
     return 0;
 }

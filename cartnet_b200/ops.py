@@ -93,9 +93,11 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- graph build
 def nlist_build(pos, cell, natoms, radius: float, pbc_mask: int = 7, batch_max_reps: bool = True,
-                want_cart: bool = True, want_i32: bool = False):
+                want_cart: bool = True, want_i32: bool = False, cells: bool = True):
     """Periodic radius graph (dataset/utils.py:57-237). Returns dict with edge_index [2,E] i64,
-    unit_cell, dist, direction (+ cart_dist, cart_dir, src32, dst32, row_ptr when requested)."""
+    unit_cell, dist, direction (+ cart_dist, cart_dir, src32, dst32, row_ptr when requested).
+    cells=True: the cell-list kernels (large crystals are binned, small ones keep the all-pairs scan inside the same
+    launches); cells=False: the all-pairs kernels for every crystal. Both give the identical, bit-exact result."""
     lib = _lib.load()
     pos = _req(pos.contiguous(), torch.float32, "pos")
     cell = _req(cell.reshape(-1, 3, 3).contiguous(), torch.float32, "cell")
@@ -112,8 +114,16 @@ def nlist_build(pos, cell, natoms, radius: float, pbc_mask: int = 7, batch_max_r
     reps_arg, stride = (reps_max, 0) if batch_max_reps else (reps, 3)
     r2 = C.c_float(float(radius) * float(radius)).value      # double product rounded to fp32 (utils.py:202)
     row_count = torch.empty(N, dtype=torch.int32, device=dev)
-    _lib.check(lib.cartnet_nlist_count(_p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2,
-                                       _p(reps_arg), stride, _p(row_count), st), "nlist_count")
+    ws = None
+    if cells and N > 0:
+        ws = torch.empty(int(lib.cartnet_nlist_cells_workspace(N, B)) // 4, dtype=torch.int32, device=dev)
+        _lib.check(lib.cartnet_nlist_cells_build(_p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, B, float(radius),
+                                                 _p(reps_arg), stride, _p(ws), st), "nlist_cells_build")
+        _lib.check(lib.cartnet_nlist_cells_count(_p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, B, float(radius), r2,
+                                                 _p(reps_arg), stride, _p(ws), _p(row_count), st), "nlist_cells_count")
+    else:
+        _lib.check(lib.cartnet_nlist_count(_p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2,
+                                           _p(reps_arg), stride, _p(row_count), st), "nlist_count")
     row_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
     _lib.check(lib.cartnet_exclusive_scan_i32(_p(row_count), N, _p(row_ptr), st), "exclusive_scan")
     E = int(row_ptr[-1].item()) if N > 0 else 0          # the one host sync: output sizes
@@ -130,10 +140,16 @@ def nlist_build(pos, cell, natoms, radius: float, pbc_mask: int = 7, batch_max_r
     if want_i32:
         out["src32"] = torch.empty(E, dtype=torch.int32, device=dev)
         out["dst32"] = torch.empty(E, dtype=torch.int32, device=dev)
-    _lib.check(lib.cartnet_nlist_fill(
-        _p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2, _p(reps_arg), stride, _p(row_ptr),
-        _p(out["edge_index"]), E, _p(out["unit_cell"]), _p(out["dist"]), _p(out["direction"]),
-        _p(out.get("cart_dist")), _p(out.get("cart_dir")), _p(out.get("src32")), _p(out.get("dst32")), st), "nlist_fill")
+    if ws is not None:
+        _lib.check(lib.cartnet_nlist_cells_fill(
+            _p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, B, float(radius), r2, _p(reps_arg), stride, _p(ws), _p(row_ptr),
+            _p(out["edge_index"]), E, _p(out["unit_cell"]), _p(out["dist"]), _p(out["direction"]),
+            _p(out.get("cart_dist")), _p(out.get("cart_dir")), _p(out.get("src32")), _p(out.get("dst32")), st), "nlist_cells_fill")
+    else:
+        _lib.check(lib.cartnet_nlist_fill(
+            _p(pos), _p(cell), _p(crystal_ptr), _p(node_crystal), N, float(radius), r2, _p(reps_arg), stride, _p(row_ptr),
+            _p(out["edge_index"]), E, _p(out["unit_cell"]), _p(out["dist"]), _p(out["direction"]),
+            _p(out.get("cart_dist")), _p(out.get("cart_dir")), _p(out.get("src32")), _p(out.get("dst32")), st), "nlist_fill")
     return out
 
 

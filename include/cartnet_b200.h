@@ -80,6 +80,28 @@ int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* cryst
                        float* direction, float* cart_dist, float* cart_dir, int32_t* src32,
                        int32_t* dst32, cartnet_stream_t stream);
 
+/* Cell-list variant of the two passes above (same outputs, same order, bit for bit) for crystals that are large against
+ * the radius: atoms are binned on a grid in wrapped fractional coordinates with bins at least r |b_k| wide, a warp per
+ * destination visits the 27 surrounding bins, tests every candidate with the reference's exact fp32 sequence and restores
+ * the reference's row order ((source, cell index) ascending, utils.py:116-123,166-170) by a rank sort of the row's keys.
+ * Crystals with fewer than 64 bins (ADP / JARVIS / MP sized cells) keep the all-pairs scan inside the same launches, so a
+ * mixed batch is one call. workspace: >= cartnet_nlist_cells_workspace(num_nodes, num_crystals) bytes, filled by _build and
+ * read by _count / _fill. */
+int64_t cartnet_nlist_cells_workspace(int32_t num_nodes, int32_t num_crystals);
+int cartnet_nlist_cells_build(const float* pos, const float* cell, const int32_t* crystal_ptr,
+                              const int32_t* node_crystal, int32_t num_nodes, int32_t num_crystals, float radius,
+                              const int32_t* reps, int32_t reps_stride, void* workspace, cartnet_stream_t stream);
+int cartnet_nlist_cells_count(const float* pos, const float* cell, const int32_t* crystal_ptr,
+                              const int32_t* node_crystal, int32_t num_nodes, int32_t num_crystals, float radius,
+                              float radius_sq, const int32_t* reps, int32_t reps_stride, const void* workspace,
+                              int32_t* row_count, cartnet_stream_t stream);
+int cartnet_nlist_cells_fill(const float* pos, const float* cell, const int32_t* crystal_ptr,
+                             const int32_t* node_crystal, int32_t num_nodes, int32_t num_crystals, float radius,
+                             float radius_sq, const int32_t* reps, int32_t reps_stride, const void* workspace,
+                             const int32_t* row_ptr, int64_t* edge_index, int64_t num_edges, float* unit_cell,
+                             float* dist, float* direction, float* cart_dist, float* cart_dir, int32_t* src32,
+                             int32_t* dst32, cartnet_stream_t stream);
+
 /* kNN neighbour cap -- replaces get_max_neighbors_mask (dataset/utils.py:240-360, call at :215-233).
  * For every destination row of a dst-sorted graph: keep[e] = 1 iff the row has <= threshold edges, or (non-strict)
  * d2[e] <= (threshold+1)-th smallest d2 of the row + tolerance (degenerate neighbours stay together), or (strict)
