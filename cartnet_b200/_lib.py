@@ -34,6 +34,11 @@ class GemmDesc(C.Structure):
     ]
 
 
+class CollateField(C.Structure):
+    """Mirror of `cartnet_collate_field_t`."""
+    _fields_ = [("src", vp), ("dst", vp), ("kind", i32), ("op", i32), ("elem_bytes", i32), ("_pad", i32)]
+
+
 class LayerDesc(C.Structure):
     """Mirror of `cartnet_layer_t` (field order must match include/cartnet_b200.h)."""
     _PTRS1 = ["src32", "dst32", "row_ptr", "col_ptr", "perm_src", "dist", "x", "e", "x_t", "e_t",
@@ -94,6 +99,10 @@ SIGNATURES = {
     "cartnet_layer_bwd": (i32, [C.POINTER(LayerDesc), vp]),
     "cartnet_cholesky_head_workspace": (i64, [i32, i32]),
     "cartnet_cholesky_head_fwd": (i32, [vp, i64, vp, vp, i32, i32, vp, vp, vp]),
+    "cartnet_collate": (i32, [C.POINTER(CollateField), i32, vp, i32, vp, i64, vp, C.POINTER(i64), vp]),
+    "cartnet_collate_close_csr": (i32, [vp, vp, i64, i64, vp]),
+    "cartnet_loss_l1_mse": (i32, [vp, vp, i64, vp, vp]),
+    "cartnet_loss_l1_mse_bwd": (i32, [vp, vp, i64, vp, vp, vp, vp]),
     "cartnet_cholesky_head_bwd": (i32, [vp, vp, i64, vp, vp, i32, i32, vp, i64, vp, vp, vp, vp]),
 }
 

@@ -69,6 +69,15 @@ def get_plan(batch) -> ops.GraphPlan:
     return plan
 
 
+def register_plan(batch, plan: ops.GraphPlan) -> None:
+    """Hands a ready-made graph plan for batch.edge_index to the cache (device-side collation builds the CSR views while
+    it assembles the batch, cartnet_b200/device_dataset.py); get_plan() then returns it without launching anything."""
+    ei = batch.edge_index
+    _plan_cache[id(ei)] = (ei, plan, ei._version)
+    while len(_plan_cache) > 4:
+        _plan_cache.popitem(last=False)
+
+
 _mask_cache: "OrderedDict[int, tuple]" = OrderedDict()
 
 

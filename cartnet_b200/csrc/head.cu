@@ -161,6 +161,43 @@ static int head_blocks(int n) {
     return b < 1 ? 1 : (b > kNumSMs / 2 ? kNumSMs / 2 : b);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// L1 / MSE loss pair of /root/reference/train/metrics.py:15-28 (nn.L1Loss + nn.MSELoss, reduction = "mean") in ONE
+// launch: a single block walks the elements in a fixed order (n ~ 60 k values at ADP-64: node-side, latency-bound), fp64
+// running sums, both means written to out[0:2]. The backward is one elementwise launch:
+// dpred = dMAE * sign(pred - true) / n + dMSE * 2 (pred - true) / n   (what autograd derives for the two modules).
+constexpr int LOSS_THREADS = 1024;
+__global__ void __launch_bounds__(LOSS_THREADS)
+loss_l1_mse_kernel(const float* __restrict__ pred, const float* __restrict__ truth, int64_t n, float* __restrict__ out) {
+    __shared__ double sm[2][LOSS_THREADS / 32];
+    double a = 0.0, q = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += LOSS_THREADS) {
+        const float d = pred[i] - truth[i];
+        a += (double)fabsf(d);
+        q += (double)d * (double)d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = a; sm[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sq = 0.0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) { sa += sm[0][w]; sq += sm[1][w]; }
+        out[0] = (float)(sa / (double)n);
+        out[1] = (float)(sq / (double)n);
+    }
+}
+
+__global__ void loss_l1_mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ truth, int64_t n,
+                                       const float* __restrict__ dmae, const float* __restrict__ dmse, float* __restrict__ dpred) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = pred[i] - truth[i];
+    const float ga = dmae ? dmae[0] : 0.f, gq = dmse ? dmse[0] : 0.f;
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    dpred[i] = (ga * sgn + gq * 2.0f * d) / (float)n;
+}
+
 }  // namespace cartnet
 
 using namespace cartnet;
@@ -214,6 +251,21 @@ int cartnet_cholesky_head_bwd(const float* dU, const float* h, int64_t ldh, cons
 #undef CN_HEAD_BWD
     CN_LAUNCH_CHECK();
     cholesky_head_final_kernel<<<ceil_div(6 * Dh + 6, 128), 128, 0, st>>>(partial, blocks, Dh, dW1, db1);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_loss_l1_mse(const float* pred, const float* truth, int64_t n, float* out2, cartnet_stream_t stream) {
+    CN_CHECK_ARG(pred && truth && out2 && n > 0, "loss_l1_mse: bad arguments");
+    loss_l1_mse_kernel<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>(pred, truth, n, out2);
+    CN_LAUNCH_CHECK();
+    return 0;
+}
+
+int cartnet_loss_l1_mse_bwd(const float* pred, const float* truth, int64_t n, const float* dmae, const float* dmse,
+                            float* dpred, cartnet_stream_t stream) {
+    CN_CHECK_ARG(pred && truth && dpred && n > 0, "loss_l1_mse_bwd: bad arguments");
+    loss_l1_mse_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, truth, n, dmae, dmse, dpred);
     CN_LAUNCH_CHECK();
     return 0;
 }

@@ -139,6 +139,33 @@ def cholesky_tail(h, W1, b1):
     return _CholeskyTailFn.apply(h, W1, b1)
 
 
+class _LossPairFn(torch.autograd.Function):
+    """(pred, true) -> (MAE, MSE), the loss pair of /root/reference/train/metrics.py:15-28, one launch forward and one
+    backward instead of nn.L1Loss + nn.MSELoss (two reductions forward, ~6 eager launches backward)."""
+
+    @staticmethod
+    def forward(ctx, pred, true):
+        p = pred.detach().contiguous().to(torch.float32)
+        t = true.detach().contiguous().to(torch.float32)
+        if p.shape != t.shape:
+            raise ValueError("compute_loss: pred %s and true %s differ in shape" % (tuple(p.shape), tuple(t.shape)))
+        out = ops.loss_l1_mse(p, t)
+        ctx.save_for_backward(p, t)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, dmae, dmse):
+        p, t = ctx.saved_tensors
+        dm = None if dmae is None else dmae.detach().reshape(1).to(torch.float32).contiguous()
+        dq = None if dmse is None else dmse.detach().reshape(1).to(torch.float32).contiguous()
+        return ops.loss_l1_mse_bwd(p, t, dm, dq), None
+
+
+def compute_loss(pred, true):
+    """Drop-in for train/metrics.py::compute_loss: returns (MAE, MSE) as 0-dim tensors with autograd through `pred`."""
+    return _LossPairFn.apply(pred, true)
+
+
 class _LayerFn(torch.autograd.Function):
     """Inputs: x [N,D], e [E,D] (fp32) and the packed weights
          W1n [4D,D] = [G1_i ; A1_i ; G1_j ; A1_j],  W1e [2D,D] = [G1_e ; A1_e],  b1 [2D] = [bg1 ; ba1],

@@ -531,3 +531,21 @@ def cholesky_head_bwd(dU, h, p6, W1):
     _lib.check(lib.cartnet_cholesky_head_bwd(_p(dU), _p(h), _ld2(h), _p(p6), _p(W1), n, Dh, _p(dh), Dh, _p(dW1), _p(db1),
                                              _p(part), _stream()), "cholesky_head_bwd")
     return dh, dW1, db1
+
+
+# ----------------------------------------------------------------------------- loss pair
+def loss_l1_mse(pred, true):
+    """(2,) fp32 = [mean |pred - true|, mean (pred - true)^2] in one launch (train/metrics.py:15-28)."""
+    lib = _lib.load()
+    _req(pred, torch.float32, "pred"); _req(true, torch.float32, "true")
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    _lib.check(lib.cartnet_loss_l1_mse(_p(pred), _p(true), int(pred.numel()), _p(out), _stream()), "loss_l1_mse")
+    return out
+
+
+def loss_l1_mse_bwd(pred, true, dmae, dmse):
+    """dpred for upstream gradients dmae / dmse (0-dim or 1-element DEVICE tensors, or None)."""
+    lib = _lib.load()
+    dpred = torch.empty_like(pred)
+    _lib.check(lib.cartnet_loss_l1_mse_bwd(_p(pred), _p(true), int(pred.numel()), _p(dmae), _p(dmse), _p(dpred), _stream()), "loss_l1_mse_bwd")
+    return dpred

@@ -383,6 +383,47 @@ int cartnet_cholesky_head_bwd(const float* dU, const float* h, int64_t ldh, cons
                               int32_t Dh, float* dh, int64_t lddh, float* dW1, float* db1, float* partial,
                               cartnet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Device-side batch assembly -- replaces PyG Batch.from_data_list / DataLoader collation on the host followed by
+ * batch.to("cuda:0") (loader/loader.py:114-124, train/train.py:169); SURVEY.md 8(f)1.
+ * The data set is resident in HBM as per-field blobs (each the concatenation of all crystals). A batch = `ids`
+ * (crystal ids, device int32 [num_selected]). Every output field is a segmented gather of the selected crystals'
+ * ranges; index-valued fields get the batch's cumulative node / edge offset added (what PyG does to edge_index).
+ *   blob_ptr  [4][blob_ptr_pitch] int32 (device): first element of every crystal in the blobs, per kind
+ *   batch_ptr [4][num_selected+1] int32 (device): first element of every selected crystal in the batch, per kind
+ *   kinds: 0 = per node, 1 = per edge, 2 = per non-H atom, 3 = per graph;  totals[kind] = elements in the batch (host).
+ * One launch assembles all fields. cartnet_collate_close_csr writes the closing entries ptr[num_nodes] = num_edges.
+ * ------------------------------------------------------------------------------------- */
+enum { CARTNET_COLLATE_PER_NODE = 0, CARTNET_COLLATE_PER_EDGE = 1, CARTNET_COLLATE_PER_NONH = 2, CARTNET_COLLATE_PER_GRAPH = 3 };
+enum {
+    CARTNET_COLLATE_COPY = 0,                 /* dst[i] = src[s]   (elem_bytes = 1 or a multiple of 4) */
+    CARTNET_COLLATE_I32_PLUS_NODE = 1,        /* int32: dst[i] = src[s] + node offset of the crystal in the batch */
+    CARTNET_COLLATE_I32_PLUS_EDGE = 2,        /* int32: dst[i] = src[s] + edge offset of the crystal in the batch */
+    CARTNET_COLLATE_I32_TO_I64_PLUS_NODE = 3, /* int32 blob -> int64 output + node offset (edge_index rows, non_H_index) */
+    CARTNET_COLLATE_SLOT_I64 = 4              /* int64: dst[i] = position of the crystal in the batch (the `batch` vector) */
+};
+typedef struct cartnet_collate_field {
+    const void* src;
+    void* dst;
+    int32_t kind, op, elem_bytes, _pad;
+} cartnet_collate_field_t;
+int cartnet_collate(const cartnet_collate_field_t* fields /* host */, int32_t num_fields, const int32_t* ids,
+                    int32_t num_selected, const int32_t* blob_ptr, int64_t blob_ptr_pitch, const int32_t* batch_ptr,
+                    const int64_t* totals /* host [4] */, cartnet_stream_t stream);
+int cartnet_collate_close_csr(int32_t* row_ptr, int32_t* col_ptr, int64_t num_nodes, int64_t num_edges,
+                              cartnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Loss pair of train/metrics.py:15-28 (nn.L1Loss and nn.MSELoss, reduction "mean") -- SURVEY.md 8(f)3.
+ *   fwd: out2[0] = mean |pred - true|, out2[1] = mean (pred - true)^2 over n contiguous fp32 values, one launch,
+ *        fixed-order fp64 sums (deterministic).
+ *   bwd: dpred = dmae[0] * sign(pred - true) / n + dmse[0] * 2 (pred - true) / n ; dmae / dmse are DEVICE scalars
+ *        (nullable = 0), so the seed of the model's backward is produced without a host round trip.
+ * ------------------------------------------------------------------------------------- */
+int cartnet_loss_l1_mse(const float* pred, const float* truth, int64_t n, float* out2, cartnet_stream_t stream);
+int cartnet_loss_l1_mse_bwd(const float* pred, const float* truth, int64_t n, const float* dmae, const float* dmse,
+                            float* dpred, cartnet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

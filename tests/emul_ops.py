@@ -265,7 +265,20 @@ def cholesky_head_bwd(dU, h, p6, W1):
     return (dp @ _f(W1)).float(), (dp.t() @ _f(h)).float(), dp.sum(0).float()
 
 
-ALL = ["cholesky_head_fwd", "cholesky_head_bwd", "graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
+def loss_l1_mse(pred, true):
+    d = pred.double() - true.double()
+    return torch.stack([d.abs().mean(), (d * d).mean()]).float()
+
+
+def loss_l1_mse_bwd(pred, true, dmae, dmse):
+    d = pred.double() - true.double()
+    n = d.numel()
+    ga = 0.0 if dmae is None else dmae.double()
+    gq = 0.0 if dmse is None else dmse.double()
+    return ((ga * torch.sign(d) + gq * 2.0 * d) / n).float()
+
+
+ALL = ["loss_l1_mse", "loss_l1_mse_bwd", "cholesky_head_fwd", "cholesky_head_bwd", "graph_plan", "edge_features", "gemm", "gemm_colstats", "gemm_tn", "colstats", "gate_center", "colsum", "edge_gate_aggregate", "node_update",
        "node_update_bwd", "edge_gate_bwd", "segment_sum", "segment_sum_pair", "dsilu_mul", "cast"]
 
 

@@ -104,6 +104,23 @@ def test_training_trajectories_of_two_fp32_implementations_diverge(monkeypatch):
     print("loss divergence oracle vs fp32 emulation:", rel)
 
 
+def test_compute_loss_matches_reference_metrics(monkeypatch):
+    """cartnet_b200.compute_loss against train/metrics.py:15-28 (nn.L1Loss / nn.MSELoss, mean) incl. gradients for
+    cfg.loss = MAE and MSE (train.py:175-183)."""
+    emul_ops.install(monkeypatch)
+    g = torch.Generator().manual_seed(0)
+    pred, true = torch.randn(37, 3, 3, generator=g), torch.randn(37, 3, 3, generator=g)
+    for which in (0, 1):
+        p1 = pred.clone().requires_grad_(True)
+        out = cartnet_b200.compute_loss(p1, true)
+        out[which].mean().backward()
+        p2 = pred.clone().requires_grad_(True)
+        ref = (torch.nn.L1Loss()(p2, true), torch.nn.MSELoss()(p2, true))
+        ref[which].mean().backward()
+        assert abs(float(out[0]) - float(ref[0])) < 1e-6 and abs(float(out[1]) - float(ref[1])) < 1e-6
+        assert torch.allclose(p1.grad, p2.grad, atol=1e-8)
+
+
 def test_unsorted_edges_give_same_result(monkeypatch):
     emul_ops.install(monkeypatch)
     shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
