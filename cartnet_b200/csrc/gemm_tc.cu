@@ -61,6 +61,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// pulls a box into L2 ahead of the demand load (no shared memory, no barrier): the A stream's first touch of a tile is a
+// DRAM access; with only 2-3 stages of shared memory per CTA the demand loads alone cannot keep enough bytes in flight
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -199,15 +204,64 @@ __device__ __forceinline__ float dsilu_fast(float z) {
 template <int EPI>
 __host__ __device__ constexpr bool epi_has(int bit, bool runtime) { return EPI == EPI_GENERIC ? runtime : ((EPI & bit) != 0); }
 
-// one float4 (4 consecutive columns) of one output row; inputs were loaded beforehand, outputs point at [row, col]
+// 8 consecutive elements of a T-typed row, unconverted: 16 bytes of bf16, 32 bytes of tf32 words, or the 16 + 16 bytes of a
+// bf16 pair run (8 elements never straddle a 64-element chunk when the column is a multiple of 8)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+template <> struct Raw8<tf32_t> { float4 a, b; };
+template <> struct Raw8<bf16p_t> { uint4 hi, lo; };
+__device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.a = __ldg(reinterpret_cast<const uint4*>(p)); return r; }
+__device__ __forceinline__ Raw8<tf32_t> ld_raw8(const tf32_t* p) {
+    Raw8<tf32_t> r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+}
+__device__ __forceinline__ Raw8<bf16p_t> ld_raw8(const bf16p_t* p) {
+    const char* h = pair_hi_addr(p);
+    Raw8<bf16p_t> r;
+    r.hi = __ldg(reinterpret_cast<const uint4*>(h));
+    r.lo = __ldg(reinterpret_cast<const uint4*>(h + 128));
+    return r;
+}
+__device__ __forceinline__ void cvt_raw8(const Raw8<__nv_bfloat16>& r, float4& v0, float4& v1) {
+    const float2 a = bf162_to_float2(r.a.x), b = bf162_to_float2(r.a.y), c = bf162_to_float2(r.a.z), d = bf162_to_float2(r.a.w);
+    v0 = make_float4(a.x, a.y, b.x, b.y);
+    v1 = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ void cvt_raw8(const Raw8<tf32_t>& r, float4& v0, float4& v1) { v0 = r.a; v1 = r.b; }
+__device__ __forceinline__ void cvt_raw8(const Raw8<bf16p_t>& r, float4& v0, float4& v1) {
+    v0 = join4_bf16(make_uint2(r.hi.x, r.hi.y), make_uint2(r.lo.x, r.lo.y));
+    v1 = join4_bf16(make_uint2(r.hi.z, r.hi.w), make_uint2(r.lo.z, r.lo.w));
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float4& v0, const float4& v1) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v0.x, v0.y), b = __floats2bfloat162_rn(v0.z, v0.w);
+    const __nv_bfloat162 c = __floats2bfloat162_rn(v1.x, v1.y), d = __floats2bfloat162_rn(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                                              *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+}
+__device__ __forceinline__ void store8(tf32_t* p, const float4& v0, const float4& v1) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(round_tf32(v0.x), round_tf32(v0.y), round_tf32(v0.z), round_tf32(v0.w));
+    reinterpret_cast<float4*>(p)[1] = make_float4(round_tf32(v1.x), round_tf32(v1.y), round_tf32(v1.z), round_tf32(v1.w));
+}
+__device__ __forceinline__ void store8(bf16p_t* p, const float4& v0, const float4& v1) {
+    uint2 h0, l0, h1, l1;
+    split4_bf16(v0, h0, l0);
+    split4_bf16(v1, h1, l1);
+    char* h = pair_hi_addr(p);
+    *reinterpret_cast<uint4*>(h) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint4*>(h + 128) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+// the arithmetic of the epilogue on 4 consecutive columns of one row (no stores): v = acc + bias + gathers; zval = v;
+// v = act(v, z_in); v += resid
 template <typename T, int EPI>
-__device__ __forceinline__ float4 epi_tc4(const EpiParams<T>& p, float4 v, const float4& bias4, bool has_g0, bool has_g1,
-                                        const float4& ga, const float4& gb, const float4& z, const float4& rs, T* z_out,
-                                        float* out_f32, T* out_t) {
+__device__ __forceinline__ void epi_math4(const EpiParams<T>& p, float4& v, float4& zval, const float4& bias4, bool has_g0, bool has_g1,
+                                          const float4& ga, const float4& gb, const float4& z, const float4& rs) {
     if (epi_has<EPI>(EB_BIAS, p.bias != nullptr)) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
     if (epi_has<EPI>(EB_GATHER, has_g0)) { v.x += ga.x; v.y += ga.y; v.z += ga.z; v.w += ga.w; }
     if (epi_has<EPI>(EB_GATHER, has_g1)) { v.x += gb.x; v.y += gb.y; v.z += gb.z; v.w += gb.w; }
-    if (epi_has<EPI>(EB_ZOUT, p.z_out != nullptr)) store4<T>(z_out, v);
+    zval = v;
     if (epi_has<EPI>(EB_SILU, p.act == CARTNET_ACT_SILU)) {
         v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
     }
@@ -215,28 +269,28 @@ __device__ __forceinline__ float4 epi_tc4(const EpiParams<T>& p, float4 v, const
         v.x *= dsilu_fast(z.x); v.y *= dsilu_fast(z.y); v.z *= dsilu_fast(z.z); v.w *= dsilu_fast(z.w);
     }
     if (epi_has<EPI>(EB_RESID, p.resid != nullptr)) { v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w; }
-    if (epi_has<EPI>(EB_OUTF, p.out_f32 != nullptr)) *reinterpret_cast<float4*>(out_f32) = v;
-    if (epi_has<EPI>(EB_OUTT, p.out_t != nullptr)) store4<T>(out_t, v);
-    return v;
 }
 
-// The 4 row groups of a warp (lane >> 3) hold partial column sums of the same 4 columns: combine them with a fixed
-// butterfly, then the owner lane (lane < 8) adds the 32-row block sums to the warp's running totals in shared memory.
-__device__ __forceinline__ void stats_flush(float* wstat, int cidx, int lane, float4 ss, float4 sq) {
+// The 8 row groups of a warp (lane >> 2) hold partial column sums of the same 8 columns: combine them with a fixed
+// butterfly, then the owner lane (lane < 4) adds the 32-row block sums to the warp's running totals in shared memory.
+__device__ __forceinline__ void stats_flush8(float* wstat, int cidx, int lane, float4* ss, float4* sq) {
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-        ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
-        ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
-        sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
-        sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
-    }
-    if (lane < 8) {
-        float4* a = reinterpret_cast<float4*>(wstat + cidx);
-        float4* b = reinterpret_cast<float4*>(wstat + 128 + cidx);
-        float4 va = *a, vb = *b;
-        va.x += ss.x; va.y += ss.y; va.z += ss.z; va.w += ss.w;
-        vb.x += sq.x; vb.y += sq.y; vb.z += sq.z; vb.w += sq.w;
-        *a = va; *b = vb;
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+            ss[h].x += __shfl_xor_sync(0xffffffffu, ss[h].x, o); ss[h].y += __shfl_xor_sync(0xffffffffu, ss[h].y, o);
+            ss[h].z += __shfl_xor_sync(0xffffffffu, ss[h].z, o); ss[h].w += __shfl_xor_sync(0xffffffffu, ss[h].w, o);
+            sq[h].x += __shfl_xor_sync(0xffffffffu, sq[h].x, o); sq[h].y += __shfl_xor_sync(0xffffffffu, sq[h].y, o);
+            sq[h].z += __shfl_xor_sync(0xffffffffu, sq[h].z, o); sq[h].w += __shfl_xor_sync(0xffffffffu, sq[h].w, o);
+        }
+        if (lane < 4) {
+            float4* a = reinterpret_cast<float4*>(wstat + cidx + 4 * h);
+            float4* b = reinterpret_cast<float4*>(wstat + 128 + cidx + 4 * h);
+            float4 va = *a, vb = *b;
+            va.x += ss[h].x; va.y += ss[h].y; va.z += ss[h].z; va.w += ss[h].w;
+            vb.x += sq[h].x; vb.y += sq[h].y; vb.z += sq[h].z; vb.w += sq[h].w;
+            *a = va; *b = vb;
+        }
     }
 }
 
@@ -260,6 +314,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              int BN, int n_tiles, int m_tiles, int stages, EpiParams<T> epi, double* __restrict__ stats) {
     using TR = TcTraits<T>;
     constexpr int NP = TR::NP;
+    const bool prefetch = (stages & 16) != 0;        // host flag folded into `stages`
+    stages &= 15;
     constexpr int KBOX = 128 / TR::TMA_ES;           // TMA elements per 128-byte box row
     constexpr int A_STAGE_BYTES = NP * NT_A_PART_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -304,6 +360,11 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t phase = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_stride) {
                 for (int kb = 0; kb < kblks; ++kb) {
+                    // L2 prefetch of the same K block of this CTA's NEXT tile (one of the CTAs that share the tile does it)
+                    if (prefetch && n_tile == 0 && mt + m_stride < m_tiles) {
+#pragma unroll
+                        for (int pt = 0; pt < NP; ++pt) tma_prefetch_2d(&tmA, (kb * NP + pt) * KBOX, (mt + m_stride) * 128);
+                    }
                     mbar_wait(&bars->a_empty[stage], phase ^ 1);
                     mbar_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
 #pragma unroll
@@ -363,12 +424,21 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c_begin = grp * cols_per_grp;
         const int c_end = (c_begin + cols_per_grp) < BN ? (c_begin + cols_per_grp) : BN;
         float* stg = smemStg + (warp - 2) * 32 * NT_STG_PITCH;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        const int sub_r = lane >> 2, sub_c = (lane & 3) * 8;       // 8 row groups x 4 column groups of 8 columns
         // EB_STATS: this warp's running column sums over all of its tiles (fp32; the caller centres the output so that
         // |mean| <~ std), one owner lane per column -> fixed order, no atomics; written out as fp64 partials at the end
         float* wstat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(NtBars) + 15) & ~(size_t)15)) + (warp - 2) * 256;
         constexpr bool kStats = EPI != EPI_GENERIC && (EPI & EB_STATS) != 0;
-        if (kStats) {
+        // pair operands: the weight slice leaves no shared memory for per-warp statistics and BN <= 128 (at most two
+        // 32-column blocks per warp), so each thread keeps the running sums of its 8 columns in registers over ALL its
+        // tiles; the 8 row groups are combined once, at the end, by the same fixed butterfly
+        constexpr bool kStatsRegs = kStats && TR::NP == 2;
+        float4 rs_s[2][2], rs_q[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) rs_s[a][h] = rs_q[a][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kStats && !kStatsRegs) {
             for (int i = lane; i < 256; i += 32) wstat[i] = 0.f;
             __syncwarp();
         }
@@ -376,12 +446,12 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles && c_begin < c_end; mt += m_stride) {
             const int64_t row0 = (int64_t)mt * 128 + q * 32;
-            // gather-row indices of the 8 output rows this thread finishes (hoisted out of the column loop)
-            int32_t i0[8], i1[8];
+            // gather-row indices of the 4 output rows this thread finishes (hoisted out of the column loop)
+            int32_t i0[4], i1[4];
             if (epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr)) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int64_t row = row0 + it * 4 + sub_r;
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t row = row0 + it * 8 + sub_r;
                     i0[it] = row < M ? epi.gidx0[row] : 0;
                     i1[it] = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
                 }
@@ -390,39 +460,36 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             bool first = true;
             for (int c = c_begin; c < c_end; c += 32) {
                 const int col = n0 + c + sub_c;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) bias4 = *reinterpret_cast<const float4*>(epi.bias + col);
+                float4 bias0 = make_float4(0.f, 0.f, 0.f, 0.f), bias1 = bias0;
+                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) {
+                    bias0 = *reinterpret_cast<const float4*>(epi.bias + col);
+                    bias1 = *reinterpret_cast<const float4*>(epi.bias + col + 4);
+                }
                 const bool has_g0 = epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr);
                 const bool has_g1 = epi_has<EPI>(EB_GATHER, epi.gather1 != nullptr);
                 const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
                 const bool has_r = epi_has<EPI>(EB_RESID, epi.resid != nullptr);
-                // phase 1: every global read of this 32x32 block is issued up front (8..24 loads in flight per thread) --
-                // before the accumulator is even fetched from TMEM, so that their L2 / HBM round trip overlaps the
-                // tcgen05.ld + shared-memory transpose (and, for a tile's first block, the wait for its MMAs) -- and
-                // before any store, whose possible aliasing would otherwise serialise the round trips.
+                // phase 1: every global read of this 32x32 block is issued up front -- before the accumulator is even
+                // fetched from TMEM, so that their L2 / HBM round trip overlaps the tcgen05.ld + shared-memory transpose
+                // (and, for a tile's first block, the wait for its MMAs) -- and before any store, whose possible aliasing
+                // would otherwise serialise the round trips. A thread owns 8 consecutive columns of 4 rows: every global
+                // access is a 16-byte vector (4 lanes cover a 32-column row segment, 8 rows per instruction).
                 // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
-                // compiler can interleave the 8 independent rows and hide the MUFU / FMA latencies.
-                typename Raw4<T>::type ra[8], rb[8], rz[8];
-                float4 rr[8];
+                // compiler can interleave the independent rows and hide the MUFU / FMA latencies.
+                Raw8<T> ra[4], rb[4], rz[4];
+                float4 rr[4][2];
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (full) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        if (has_g0) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                        if (has_g1) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                        if (has_z) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
-                        if (has_r) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
-                    }
-                } else {
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        const bool ok = row < M;
-                        if (has_g0 && ok) ra[it] = ld_raw4<T>(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                        if (has_g1 && ok) rb[it] = ld_raw4<T>(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                        if (has_z && ok) rz[it] = ld_raw4<T>(epi.z_in + row * epi.ldzin + col);
-                        if (has_r && ok) rr[it] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t row = row0 + it * 8 + sub_r;
+                    if (full || row < M) {
+                        if (has_g0) ra[it] = ld_raw8(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
+                        if (has_g1) rb[it] = ld_raw8(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
+                        if (has_z) rz[it] = ld_raw8(epi.z_in + row * epi.ldzin + col);
+                        if (has_r) {
+                            rr[it][0] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
+                            rr[it][1] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col + 4));
+                        }
                     }
                 }
                 if (first) {
@@ -436,44 +503,55 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                float4 t4[8];
+                float4 t8[4][2];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int srow = it * 4 + sub_r;
-                    t4[it] = *reinterpret_cast<const float4*>(stg + srow * NT_STG_PITCH + 4 * ((sub_c >> 2) ^ (srow & 7)));
+                for (int it = 0; it < 4; ++it) {
+                    const int srow = it * 8 + sub_r;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        t8[it][h] = *reinterpret_cast<const float4*>(stg + srow * NT_STG_PITCH + 4 * (((sub_c >> 2) + h) ^ (srow & 7)));
                 }
                 __syncwarp();
-                float4 ss = zero, sq = zero;
-                if (full) {
+                float4 ss[2] = {zero, zero}, sq[2] = {zero, zero};
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        const float4 o = epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
-                                                         has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
-                                                         epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
-                                                         epi.out_t + row * epi.ldt + col);
-                        if (kStats) {
-                            ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
-                            sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t row = row0 + it * 8 + sub_r;
+                    if (full || row < M) {
+                        float4 ga0 = zero, ga1 = zero, gb0 = zero, gb1 = zero, z0 = zero, z1 = zero, zv0, zv1;
+                        if (has_g0) cvt_raw8(ra[it], ga0, ga1);
+                        if (has_g1) cvt_raw8(rb[it], gb0, gb1);
+                        if (has_z) cvt_raw8(rz[it], z0, z1);
+                        float4 o0 = t8[it][0], o1 = t8[it][1];
+                        epi_math4<T, EPI>(epi, o0, zv0, bias0, has_g0, has_g1, ga0, gb0, z0, has_r ? rr[it][0] : zero);
+                        epi_math4<T, EPI>(epi, o1, zv1, bias1, has_g0, has_g1, ga1, gb1, z1, has_r ? rr[it][1] : zero);
+                        if (epi_has<EPI>(EB_ZOUT, epi.z_out != nullptr)) store8(epi.z_out + row * epi.ldz + col, zv0, zv1);
+                        if (epi_has<EPI>(EB_OUTF, epi.out_f32 != nullptr)) {
+                            *reinterpret_cast<float4*>(epi.out_f32 + row * epi.ldo + col) = o0;
+                            *reinterpret_cast<float4*>(epi.out_f32 + row * epi.ldo + col + 4) = o1;
                         }
-                    }
-                } else {
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int64_t row = row0 + it * 4 + sub_r;
-                        if (row < M) {
-                            const float4 o = epi_tc4<T, EPI>(epi, t4[it], bias4, has_g0, has_g1, has_g0 ? cvt_raw4(ra[it]) : zero,
-                                                             has_g1 ? cvt_raw4(rb[it]) : zero, has_z ? cvt_raw4(rz[it]) : zero, has_r ? rr[it] : zero,
-                                                             epi.z_out + row * epi.ldz + col, epi.out_f32 + row * epi.ldo + col,
-                                                             epi.out_t + row * epi.ldt + col);
-                            if (kStats) {
-                                ss.x += o.x; ss.y += o.y; ss.z += o.z; ss.w += o.w;
-                                sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y); sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
-                            }
+                        if (epi_has<EPI>(EB_OUTT, epi.out_t != nullptr)) store8(epi.out_t + row * epi.ldt + col, o0, o1);
+                        if (kStats) {
+                            ss[0].x += o0.x; ss[0].y += o0.y; ss[0].z += o0.z; ss[0].w += o0.w;
+                            ss[1].x += o1.x; ss[1].y += o1.y; ss[1].z += o1.z; ss[1].w += o1.w;
+                            sq[0].x = fmaf(o0.x, o0.x, sq[0].x); sq[0].y = fmaf(o0.y, o0.y, sq[0].y); sq[0].z = fmaf(o0.z, o0.z, sq[0].z); sq[0].w = fmaf(o0.w, o0.w, sq[0].w);
+                            sq[1].x = fmaf(o1.x, o1.x, sq[1].x); sq[1].y = fmaf(o1.y, o1.y, sq[1].y); sq[1].z = fmaf(o1.z, o1.z, sq[1].z); sq[1].w = fmaf(o1.w, o1.w, sq[1].w);
                         }
                     }
                 }
-                if (kStats) stats_flush(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
+                if (kStatsRegs) {
+                    const int cb = (c - c_begin) >> 5;          // 0 or 1
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+                        if (a == cb) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                rs_s[a][h].x += ss[h].x; rs_s[a][h].y += ss[h].y; rs_s[a][h].z += ss[h].z; rs_s[a][h].w += ss[h].w;
+                                rs_q[a][h].x += sq[h].x; rs_q[a][h].y += sq[h].y; rs_q[a][h].z += sq[h].z; rs_q[a][h].w += sq[h].w;
+                            }
+                        }
+                } else if (kStats) {
+                    stats_flush8(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -481,7 +559,30 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (kStats) {
+        if (kStatsRegs) {
+            const int64_t blk = (int64_t)(blockIdx.x / n_tiles) * 4 + q;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                if (c_begin + 32 * a >= c_end) break;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int o = 4; o <= 16; o <<= 1) {
+                        rs_s[a][h].x += __shfl_xor_sync(0xffffffffu, rs_s[a][h].x, o); rs_s[a][h].y += __shfl_xor_sync(0xffffffffu, rs_s[a][h].y, o);
+                        rs_s[a][h].z += __shfl_xor_sync(0xffffffffu, rs_s[a][h].z, o); rs_s[a][h].w += __shfl_xor_sync(0xffffffffu, rs_s[a][h].w, o);
+                        rs_q[a][h].x += __shfl_xor_sync(0xffffffffu, rs_q[a][h].x, o); rs_q[a][h].y += __shfl_xor_sync(0xffffffffu, rs_q[a][h].y, o);
+                        rs_q[a][h].z += __shfl_xor_sync(0xffffffffu, rs_q[a][h].z, o); rs_q[a][h].w += __shfl_xor_sync(0xffffffffu, rs_q[a][h].w, o);
+                    }
+                    if (lane < 4) {
+                        const int64_t cg = n0 + c_begin + 32 * a + sub_c + 4 * h;
+                        double* ps = stats + (blk * 2 + 0) * N + cg;
+                        double* pq = stats + (blk * 2 + 1) * N + cg;
+                        ps[0] = (double)rs_s[a][h].x; ps[1] = (double)rs_s[a][h].y; ps[2] = (double)rs_s[a][h].z; ps[3] = (double)rs_s[a][h].w;
+                        pq[0] = (double)rs_q[a][h].x; pq[1] = (double)rs_q[a][h].y; pq[2] = (double)rs_q[a][h].z; pq[3] = (double)rs_q[a][h].w;
+                    }
+                }
+            }
+        } else if (kStats) {
             // one partial row per (m-CTA, TMEM lane quarter): [blk][sum | sumsq][N] fp64, summed in a fixed order afterwards
             __syncwarp();
             const int64_t blk = (int64_t)(blockIdx.x / n_tiles) * 4 + q;
@@ -685,11 +786,12 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     int BN = 0, stages = 0;
     size_t smem = 0;
     static const int bn_cap = getenv("CARTNET_NT_BN_CAP") ? atoi(getenv("CARTNET_NT_BN_CAP")) : 256;   // tuning knob (experiments)
+    const bool stats_in_regs = stats && NP == 2;            // pairs: per-thread running sums, at most two column blocks per warp
     for (int cand : {256, 128, 64, 32}) {
-        if (cand > bn_cap || (int64_t)cand * d.K * slot > 131072 || d.N % cand != 0) continue;
+        if (cand > bn_cap || (int64_t)cand * d.K * slot > 131072 || d.N % cand != 0 || (stats_in_regs && cand > 128)) continue;
         for (int ns : {NT_STAGES, 2}) {
             const size_t need = 1024 + (size_t)cand * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
-                                (stats ? NT_STAT_BYTES : 0);
+                                ((stats && !stats_in_regs) ? NT_STAT_BYTES : 0);
             if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; break; }
         }
         if (BN) break;
@@ -705,6 +807,8 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     rc = make_map(&tmB, TR::DT, TR::TMA_ES, d.B, d.N, (int64_t)NP * d.K, NP * d.ldb, 128 / TR::TMA_ES, BN);
     if (rc) return rc;
     if (stats_blocks) *stats_blocks = (grid / n_tiles) * 4;
+    static const int pf_env = getenv("CARTNET_NT_PREFETCH") ? atoi(getenv("CARTNET_NT_PREFETCH")) : 1;     // tuning knob (experiments)
+    if (pf_env && m_tiles > grid / n_tiles) stages |= 16;
     int mask = 0;
     if (stats) mask |= EB_STATS;
     if (d.bias) mask |= EB_BIAS;
