@@ -8,12 +8,17 @@
 
 namespace cartnet {
 
+// element type of the gathered projections: T, except for bf16 pairs -- the projections are only ever ADDED in the
+// epilogue, never contracted, so the split-precision mode keeps them as plain fp32 words (exact, and no hi + lo join per use)
+template <typename T> struct GatherOf { using type = T; };
+template <> struct GatherOf<bf16p_t> { using type = tf32_t; };
+
 template <typename T>
 struct EpiParams {
     const float* bias;
-    const T* gather0;
+    const typename GatherOf<T>::type* gather0;
     const int32_t* gidx0;
-    const T* gather1;
+    const typename GatherOf<T>::type* gather1;
     const int32_t* gidx1;
     int64_t ldg;
     T* z_out;
@@ -33,8 +38,8 @@ template <typename T>
 inline EpiParams<T> make_epi(const cartnet_gemm_t& d) {
     EpiParams<T> p;
     p.bias = d.bias;
-    p.gather0 = (const T*)d.gather0; p.gidx0 = d.gidx0;
-    p.gather1 = (const T*)d.gather1; p.gidx1 = d.gidx1;
+    p.gather0 = (const typename GatherOf<T>::type*)d.gather0; p.gidx0 = d.gidx0;
+    p.gather1 = (const typename GatherOf<T>::type*)d.gather1; p.gidx1 = d.gidx1;
     p.ldg = d.ldg;
     p.z_out = (T*)d.z_out; p.ldz = d.ldz;
     p.act = d.act;
@@ -48,8 +53,8 @@ inline EpiParams<T> make_epi(const cartnet_gemm_t& d) {
 // per-row gather bases are resolved once per row by the caller
 template <typename T>
 struct EpiRow {
-    const T* g0;   // gather0 + gidx0[row]*ldg  (or null)
-    const T* g1;
+    const typename GatherOf<T>::type* g0;   // gather0 + gidx0[row]*ldg  (or null)
+    const typename GatherOf<T>::type* g1;
 };
 
 template <typename T>

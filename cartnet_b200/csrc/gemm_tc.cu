@@ -476,7 +476,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 // access is a 16-byte vector (4 lanes cover a 32-column row segment, 8 rows per instruction).
                 // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
                 // compiler can interleave the independent rows and hide the MUFU / FMA latencies.
-                Raw8<T> ra[4], rb[4], rz[4];
+                Raw8<typename GatherOf<T>::type> ra[4], rb[4];
+                Raw8<T> rz[4];
                 float4 rr[4][2];
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

@@ -110,7 +110,8 @@ int cartnet_layer_fwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     // per-node projections P = x W1n^T : [:, 0:2D] dst-role (gate|aggr), [:, 2D:4D] src-role
     {
         cartnet_gemm_t d = gemm_desc(prec, N, 4 * D, D, L->x_t, D, L->W1n_t, D);
-        d.out_t = L->P; d.ldt = 4 * D;
+        if (prec == CARTNET_PREC_BF16X3) { d.out_f32 = (float*)L->P; d.ldo = 4 * D; }      // gathered operands stay plain fp32 (see cartnet_gemm_t)
+        else { d.out_t = L->P; d.ldt = 4 * D; }
         CN_TRY(cartnet_gemm(&d, st));
     }
     // per-edge first Linear with gathered projections + SiLU                         (cartnet.py:237,256)

@@ -193,9 +193,12 @@ constexpr int kMinBins = 64;
 constexpr int kRowCap = 1024;
 
 struct CrystalGrid {      // per crystal, in the workspace
+    CellGeom g;           // computed once per crystal (fp64 inverse, image half-ranges): fp64 is slow on this part, and
+                          // recomputing it in every warp was ~40 % of the XU pipe of the all-pairs kernels
     int32_t nb[3];        // bins per axis (0 = all-pairs path)
     int32_t bin0;         // first bin of this crystal in the global bin arrays
 };
+constexpr int kGridWords = (int)((sizeof(CrystalGrid) + 3) / 4);
 
 __global__ void grid_setup_kernel(const float* __restrict__ cell, const int32_t* __restrict__ crystal_ptr, int num_crystals,
                                   float radius, const int32_t* __restrict__ reps, int reps_stride, CrystalGrid* __restrict__ grids) {
@@ -219,6 +222,7 @@ __global__ void grid_setup_kernel(const float* __restrict__ cell, const int32_t*
     const int64_t ncells = (int64_t)(2 * g.rep[0] + 1) * (2 * g.rep[1] + 1) * (2 * g.rep[2] + 1);
     const bool use = nb[0] >= 1 && nb[1] >= 1 && nb[2] >= 1 && (int64_t)nb[0] * nb[1] * nb[2] >= kMinBins && (int64_t)nb[0] * nb[1] * nb[2] <= n &&
                      ncells <= 1024 && n < (1 << 22);          // row keys pack (source, cell) into 22 + 10 bits
+    grids[b].g = g;
     grids[b].nb[0] = use ? nb[0] : 0; grids[b].nb[1] = use ? nb[1] : 0; grids[b].nb[2] = use ? nb[2] : 0;
     grids[b].bin0 = crystal_ptr[b];          // bins of crystal b live at [crystal_ptr[b], crystal_ptr[b] + nb0*nb1*nb2) (<= its atom count)
 }
@@ -242,10 +246,9 @@ __global__ void bin_atoms_kernel(const float* __restrict__ pos, const float* __r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_nodes) return;
     const int b = node_crystal[i];
-    const CrystalGrid gr = grids[b];
-    if (gr.nb[0] == 0) { atom_bin[i] = -1; return; }
-    CellGeom g;
-    load_geom(g, cell, reps, reps_stride, b, radius);
+    if (grids[b].nb[0] == 0) { atom_bin[i] = -1; return; }
+    const CrystalGrid& gr = grids[b];
+    const CellGeom& g = gr.g;
     const float p[3] = {pos[3 * (int64_t)i], pos[3 * (int64_t)i + 1], pos[3 * (int64_t)i + 2]};
     int bin[3], shift[3];
     frac_bin(g, p, gr.nb, bin, shift);
@@ -276,9 +279,8 @@ nlist_cells_kernel(const float* __restrict__ pos, const float* __restrict__ cell
     if (i1 >= num_nodes) return;
     const int b = node_crystal[i1];
     const int a0 = crystal_ptr[b], a1 = crystal_ptr[b + 1];
-    CellGeom g;
-    load_geom(g, cell, reps, reps_stride, b, radius);
-    const CrystalGrid gr = grids[b];
+    const CrystalGrid gr = grids[b];             // per-crystal geometry precomputed by grid_setup_kernel
+    const CellGeom& g = gr.g;
     const int64_t out_base = FILL ? (int64_t)row_ptr[i1] : 0;
     const int row_len = FILL ? row_ptr[i1 + 1] - row_ptr[i1] : 0;
     if (gr.nb[0] == 0 || (FILL && row_len > kRowCap)) {
@@ -604,8 +606,8 @@ int cartnet_nlist_fill(const float* pos, const float* cell, const int32_t* cryst
     return 0;
 }
 
-// workspace layout (int32 words): grids [4 B] | atom_bin [N] | bin_count / cursor [N + 1] | bin_ptr [N + 2] | bin_atoms [N]
-static inline int64_t cells_ws_words(int64_t N, int64_t B) { return 4 * B + N + (N + 1) + (N + 2) + N + 16; }
+// workspace layout (int32 words): grids [kGridWords B] | atom_bin [N] | bin_count / cursor [N + 1] | bin_ptr [N + 2] | bin_atoms [N]
+static inline int64_t cells_ws_words(int64_t N, int64_t B) { return (int64_t)kGridWords * B + 2 + N + (N + 1) + (N + 2) + N + 16; }
 
 int64_t cartnet_nlist_cells_workspace(int32_t num_nodes, int32_t num_crystals) {
     return cells_ws_words(num_nodes, num_crystals) * (int64_t)sizeof(int32_t);
@@ -618,7 +620,7 @@ struct CellsWs {
 static inline CellsWs cells_ws(void* ws, int64_t N, int64_t B) {
     int32_t* w = (int32_t*)ws;
     CellsWs c;
-    c.grids = (CrystalGrid*)w; w += 4 * B;
+    c.grids = (CrystalGrid*)w; w += ((int64_t)kGridWords * B + 1) & ~(int64_t)1;      // keeps the arrays behind it 8-byte aligned
     c.atom_bin = w; w += N;
     c.bin_count = w; w += N + 1;
     c.bin_ptr = w; w += N + 2;

@@ -192,7 +192,10 @@ class _LayerFn(torch.autograd.Function):
 
         # per-node projections P = x W1n^T : [:, 0:2D] dst-role (gate|aggr), [:, 2D:4D] src-role
         P = torch.empty(N, 4 * D, dtype=T, device=dev)
-        ops.gemm(prec, x_t, W1n_t, out_t=P)
+        if prec == PREC_BF16X3:
+            ops.gemm(prec, x_t, W1n_t, out_f32=P)       # gathered operands are plain fp32 in this mode (only added, never contracted)
+        else:
+            ops.gemm(prec, x_t, W1n_t, out_t=P)
         # per-edge first Linear with gathered projections, SiLU                       (cartnet.py:237,256)
         Z = torch.empty(E, 2 * D, dtype=T, device=dev)
         H = torch.empty(E, 2 * D, dtype=T, device=dev)

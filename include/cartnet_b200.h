@@ -153,7 +153,7 @@ typedef struct cartnet_gemm {
     int64_t ldb;
     /* epilogue, applied in this order; null pointer = step skipped */
     const float* bias;       /* v += bias[col] */
-    const void* gather0;     /* v += gather0[gidx0[row]*ldg + col]      (T) */
+    const void* gather0;     /* v += gather0[gidx0[row]*ldg + col]      (T; plain fp32 in the BF16X3 mode: only added, never contracted) */
     const int32_t* gidx0;
     const void* gather1;     /* v += gather1[gidx1[row]*ldg + col]      (T) */
     const int32_t* gidx1;

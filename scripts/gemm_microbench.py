@@ -43,7 +43,8 @@ def nt(M, Nn, K, mode):
     elif mode == "tout":
         kw = dict(out_t=torch.empty(M, Nn, device=dev, dtype=T))
     elif mode.startswith("gather_silu"):
-        P = tt(torch.randn(N, 2 * Nn, device=dev))
+        P = torch.randn(N, 2 * Nn, device=dev)
+        P = P if prec == ops.PREC_BF16X3 else tt(P)          # bf16x3: gathered operands are plain fp32
         dst = torch.sort(torch.randint(0, N, (M,), device=dev))[0].to(torch.int32)
         src = torch.randint(0, N, (M,), device=dev, dtype=torch.int32)
         if mode == "gather_silu_same":      # both gathers hit one row: L1-resident (isolates the gather path)

@@ -75,7 +75,7 @@ def test_gemm_fused_epilogues():
     o_r = torch.empty(M, N)
     EM.gemm(X3, A, B, resid=resid, out_f32=o_r)
     # device
-    Ag, Bg, Pg = pack(A), pack(B), pack(P)
+    Ag, Bg, Pg = pack(A), pack(B), P.cuda()          # gathered operands are plain fp32 in this mode
     z = torch.empty(M, N, dtype=torch.float32, device="cuda")
     h = torch.empty(M, N, dtype=torch.float32, device="cuda")
     ops.gemm(X3, Ag, Bg, bias=bias.cuda(), gather0=Pg[:, :N], gidx0=i0.cuda(), gather1=Pg[:, N:], gidx1=i1.cuda(), z_out=z,
