@@ -223,17 +223,21 @@ struct SumF {
     __device__ void finish(int, double (*)[4]) const {}
 };
 // y = (T)(dy * silu'(z)) written on the fly, column sums of y (a bias gradient) as the reduction
+// z (a pre-activation) is only ever used elementwise: plain fp32 words in the bf16 pair mode (gemm_epilogue.cuh::GatherOf)
+template <typename T> struct ZOf { using type = T; };
+template <> struct ZOf<bf16p_t> { using type = float; };
+
 template <typename T>
 struct DsiluMulF {
     static constexpr int NV = 1;
     static constexpr bool F32_PARTIAL = true;
     using State = NoState;
     struct In { float4 d, z; };
-    const float* dy; int64_t ld_dy; const T* z; int64_t ldz; T* y; int64_t ldy;
+    const float* dy; int64_t ld_dy; const typename ZOf<T>::type* z; int64_t ldz; T* y; int64_t ldy;
     __device__ State init(int) const { return State{}; }
     __device__ void load(int64_t r, int col, In& in) const {
         in.d = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + col));
-        in.z = ldg4<T>(z + r * ldz + col);
+        in.z = ldg4<typename ZOf<T>::type>(z + r * ldz + col);
     }
     __device__ void compute(const State&, int64_t r, int col, const In& in, float4* o) const {
         const float4 v = make_float4(in.d.x * dsiluf_(in.z.x), in.d.y * dsiluf_(in.z.y), in.d.z * dsiluf_(in.z.z), in.d.w * dsiluf_(in.z.w));
@@ -486,13 +490,22 @@ template <typename T> struct Vec16 {
     }
     static __device__ __forceinline__ void store(T* p, const float* v) { store4<T>(p, make_float4(v[0], v[1], v[2], v[3])); }
 };
-template <> struct Vec16<bf16p_t> {
-    static constexpr int N = 4;
+template <> struct Vec16<bf16p_t> {      // 8 elements: 16 bytes of high parts + 16 bytes of low parts
+    static constexpr int N = 8;
     static __device__ __forceinline__ void load(const bf16p_t* p, float* v) {
-        const float4 r = ldg4<bf16p_t>(p);
-        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+        const char* h = pair_hi_addr(p);
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(h)), lo = __ldg(reinterpret_cast<const uint4*>(h + 128));
+        const float4 a = join4_bf16(make_uint2(hi.x, hi.y), make_uint2(lo.x, lo.y)), b = join4_bf16(make_uint2(hi.z, hi.w), make_uint2(lo.z, lo.w));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    static __device__ __forceinline__ void store(bf16p_t* p, const float* v) { store4<bf16p_t>(p, make_float4(v[0], v[1], v[2], v[3])); }
+    static __device__ __forceinline__ void store(bf16p_t* p, const float* v) {
+        uint2 h0, l0, h1, l1;
+        split4_bf16(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+        split4_bf16(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+        char* h = pair_hi_addr(p);
+        *reinterpret_cast<uint4*>(h) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(h + 128) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    }
 };
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int N = 8;
@@ -661,7 +674,7 @@ segment_sum_pair_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __r
 }
 
 template <typename T>
-__global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, const T* __restrict__ z, int64_t ldz,
+__global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, const typename ZOf<T>::type* __restrict__ z, int64_t ldz,
                                  T* __restrict__ y, int64_t ldy, int64_t rows, int C) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int c4 = C >> 2;
@@ -669,7 +682,7 @@ __global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, co
     const int64_t r = i / c4;
     const int col = (int)(i % c4) * 4;
     const float4 d = *reinterpret_cast<const float4*>(dy + r * ld_dy + col);
-    const float4 zz = load4<T>(z + r * ldz + col);
+    const float4 zz = load4<typename ZOf<T>::type>(z + r * ldz + col);
     store4<T>(y + r * ldy + col, make_float4(d.x * dsiluf_(zz.x), d.y * dsiluf_(zz.y), d.z * dsiluf_(zz.z), d.w * dsiluf_(zz.w)));
 }
 
@@ -1012,13 +1025,13 @@ int cartnet_dsilu_mul(const float* dy, int64_t ld_dy, const void* z, int64_t ldz
     if (colsum) {      // one pass: the column sums of y ride along (fp64 partials, fixed order)
         CN_CHECK_ARG(partial && colreduce_shape_ok(C), "dsilu_mul: column sums need a workspace and C/4 a power of two <= 256 (C=%d)", C);
         CN_DISPATCH_PREC(prec, {
-            DsiluMulF<T> f{dy, ld_dy, (const T*)z, ldz, (T*)y, ldy};
+            DsiluMulF<T> f{dy, ld_dy, (const typename ZOf<T>::type*)z, ldz, (T*)y, ldy};
             return run_colreduce(f, rows, C, partial, FIN_SUMS, colsum, nullptr, nullptr, nullptr, 0.f, C, st);
         });
     }
     const int64_t total = rows * (C / 4);
     CN_DISPATCH_PREC(prec, {
-        dsilu_mul_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(dy, ld_dy, (const T*)z, ldz, (T*)y, ldy, rows, C);
+        dsilu_mul_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(dy, ld_dy, (const typename ZOf<T>::type*)z, ldz, (T*)y, ldy, rows, C);
     });
     CN_LAUNCH_CHECK();
     return 0;

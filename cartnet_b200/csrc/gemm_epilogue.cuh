@@ -8,10 +8,12 @@
 
 namespace cartnet {
 
-// element type of the gathered projections: T, except for bf16 pairs -- the projections are only ever ADDED in the
-// epilogue, never contracted, so the split-precision mode keeps them as plain fp32 words (exact, and no hi + lo join per use)
+// element type of the tensors that the epilogue only touches ELEMENTWISE -- the gathered projections (added) and the
+// pre-activations z (stored for, and read by, the SiLU' of the backward pass): T, except for bf16 pairs, where they are
+// plain fp32 words. They are never contracted, so a hi|lo pair would cost the same 4 bytes, be less exact, and need a
+// split on every store and a join on every load.
 template <typename T> struct GatherOf { using type = T; };
-template <> struct GatherOf<bf16p_t> { using type = tf32_t; };
+template <> struct GatherOf<bf16p_t> { using type = float; };
 
 template <typename T>
 struct EpiParams {
@@ -21,10 +23,10 @@ struct EpiParams {
     const typename GatherOf<T>::type* gather1;
     const int32_t* gidx1;
     int64_t ldg;
-    T* z_out;
+    typename GatherOf<T>::type* z_out;
     int64_t ldz;
     int act;
-    const T* z_in;
+    const typename GatherOf<T>::type* z_in;
     int64_t ldzin;
     const float* resid;
     int64_t ldr;
@@ -41,9 +43,9 @@ inline EpiParams<T> make_epi(const cartnet_gemm_t& d) {
     p.gather0 = (const typename GatherOf<T>::type*)d.gather0; p.gidx0 = d.gidx0;
     p.gather1 = (const typename GatherOf<T>::type*)d.gather1; p.gidx1 = d.gidx1;
     p.ldg = d.ldg;
-    p.z_out = (T*)d.z_out; p.ldz = d.ldz;
+    p.z_out = (typename GatherOf<T>::type*)d.z_out; p.ldz = d.ldz;
     p.act = d.act;
-    p.z_in = (const T*)d.z_in; p.ldzin = d.ldzin;
+    p.z_in = (const typename GatherOf<T>::type*)d.z_in; p.ldzin = d.ldzin;
     p.resid = d.resid; p.ldr = d.ldr;
     p.out_f32 = d.out_f32; p.ldo = d.ldo;
     p.out_t = (T*)d.out_t; p.ldt = d.ldt;

@@ -209,10 +209,17 @@ __host__ __device__ constexpr bool epi_has(int bit, bool runtime) { return EPI =
 template <typename T> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> { uint4 a; };
 template <> struct Raw8<tf32_t> { float4 a, b; };
+template <> struct Raw8<float> { float4 a, b; };
 template <> struct Raw8<bf16p_t> { uint4 hi, lo; };
 __device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.a = __ldg(reinterpret_cast<const uint4*>(p)); return r; }
 __device__ __forceinline__ Raw8<tf32_t> ld_raw8(const tf32_t* p) {
     Raw8<tf32_t> r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+}
+__device__ __forceinline__ Raw8<float> ld_raw8(const float* p) {
+    Raw8<float> r;
     r.a = __ldg(reinterpret_cast<const float4*>(p));
     r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     return r;
@@ -230,6 +237,7 @@ __device__ __forceinline__ void cvt_raw8(const Raw8<__nv_bfloat16>& r, float4& v
     v1 = make_float4(c.x, c.y, d.x, d.y);
 }
 __device__ __forceinline__ void cvt_raw8(const Raw8<tf32_t>& r, float4& v0, float4& v1) { v0 = r.a; v1 = r.b; }
+__device__ __forceinline__ void cvt_raw8(const Raw8<float>& r, float4& v0, float4& v1) { v0 = r.a; v1 = r.b; }
 __device__ __forceinline__ void cvt_raw8(const Raw8<bf16p_t>& r, float4& v0, float4& v1) {
     v0 = join4_bf16(make_uint2(r.hi.x, r.hi.y), make_uint2(r.lo.x, r.lo.y));
     v1 = join4_bf16(make_uint2(r.hi.z, r.hi.w), make_uint2(r.lo.z, r.lo.w));
@@ -243,6 +251,10 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float4& v0, const
 __device__ __forceinline__ void store8(tf32_t* p, const float4& v0, const float4& v1) {
     reinterpret_cast<float4*>(p)[0] = make_float4(round_tf32(v0.x), round_tf32(v0.y), round_tf32(v0.z), round_tf32(v0.w));
     reinterpret_cast<float4*>(p)[1] = make_float4(round_tf32(v1.x), round_tf32(v1.y), round_tf32(v1.z), round_tf32(v1.w));
+}
+__device__ __forceinline__ void store8(float* p, const float4& v0, const float4& v1) {
+    reinterpret_cast<float4*>(p)[0] = v0;
+    reinterpret_cast<float4*>(p)[1] = v1;
 }
 __device__ __forceinline__ void store8(bf16p_t* p, const float4& v0, const float4& v1) {
     uint2 h0, l0, h1, l1;
@@ -476,8 +488,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 // access is a 16-byte vector (4 lanes cover a 32-column row segment, 8 rows per instruction).
                 // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
                 // compiler can interleave the independent rows and hide the MUFU / FMA latencies.
-                Raw8<typename GatherOf<T>::type> ra[4], rb[4];
-                Raw8<T> rz[4];
+                Raw8<typename GatherOf<T>::type> ra[4], rb[4], rz[4];
                 float4 rr[4][2];
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

@@ -158,11 +158,11 @@ typedef struct cartnet_gemm {
     const void* gather1;     /* v += gather1[gidx1[row]*ldg + col]      (T) */
     const int32_t* gidx1;
     int64_t ldg;
-    void* z_out;             /* z_out[row*ldz + col] = v                (T) */
+    void* z_out;             /* z_out[row*ldz + col] = v                (T; plain fp32 in the BF16X3 mode, like gather*) */
     int64_t ldz;
     int32_t act;             /* CARTNET_ACT_*: none | v = silu(v) | v *= silu'(z_in[row*ldzin+col]) */
     int32_t _pad;
-    const void* z_in;        /* T */
+    const void* z_in;        /* T (plain fp32 in the BF16X3 mode) */
     int64_t ldzin;
     const float* resid;      /* v += resid[row*ldr + col] */
     int64_t ldr;

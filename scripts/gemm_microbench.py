@@ -58,7 +58,7 @@ def nt(M, Nn, K, mode):
     elif mode == "bias_tout":
         kw = dict(bias=torch.randn(Nn, device=dev), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     elif mode == "dsilu":
-        kw = dict(act=ops.ACT_MUL_DSILU, z_in=tt(torch.randn(M, Nn, device=dev)), out_t=torch.empty(M, Nn, device=dev, dtype=T))
+        kw = dict(act=ops.ACT_MUL_DSILU, z_in=(torch.randn(M, Nn, device=dev) if prec == ops.PREC_BF16X3 else tt(torch.randn(M, Nn, device=dev))), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     ms = timeit(lambda: ops.gemm(prec, A, B, **kw), reps)
     print("NT  M=%7d N=%4d K=%4d %-12s %8.3f ms  %7.1f TFLOP/s" % (M, Nn, K, mode, ms, 2.0 * M * Nn * K / ms / 1e9))
 
