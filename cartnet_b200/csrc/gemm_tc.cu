@@ -849,6 +849,10 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     CN_NT_CASE(EB_DSILU | EB_OUTT)                                        // dgrad through the second Linears
     CN_NT_CASE(EB_RESID | EB_OUTF)                                        // dgrad to e / x with the residual
     CN_NT_CASE(EB_OUTF)                                                   // dgrad to e when no gradient enters e_out (last layer)
+    CN_NT_CASE(EB_BIAS | EB_GATHER | EB_SILU | EB_OUTT)                   // inference (no backward): the pre-activations are not stored
+    CN_NT_CASE(EB_BIAS | EB_SILU | EB_OUTT)
+    CN_NT_CASE(EB_BIAS | EB_SILU | EB_OUTF | EB_OUTT)
+    CN_NT_CASE(EB_BIAS | EB_SILU | EB_OUTF)
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTT)                     // edge encoder, first Linear
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF | EB_OUTT)           // edge encoder, second Linear (bf16)
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF)                     // edge encoder, second Linear (tf32)

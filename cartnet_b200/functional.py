@@ -44,15 +44,17 @@ class _EdgeEncoderFn(torch.autograd.Function):
         feat = ops.edge_features(cart_dist, cart_dir, means, betas, upper, invariant, KF, prec)
         Wa_t = _to_t(F.pad(Wa.detach(), (0, KF - dim_edge)), prec)
         Wb_t = _to_t(Wb, prec)
-        Z1 = torch.empty(E, D2, dtype=T, device=dev)
+        need_bwd = any(ctx.needs_input_grad)       # inference (torch.no_grad): the pre-activations are never read -- not stored
+        Z1 = torch.empty(E, D2, dtype=T, device=dev) if need_bwd else None
         H1 = torch.empty(E, D2, dtype=T, device=dev)
         ops.gemm(prec, feat, Wa_t, bias=ba.detach(), z_out=Z1, act=ACT_SILU, out_t=H1)
-        Z2 = torch.empty(E, D, dtype=T, device=dev)
+        Z2 = torch.empty(E, D, dtype=T, device=dev) if need_bwd else None
         e0 = torch.empty(E, D, dtype=torch.float32, device=dev)
         e0_t = torch.empty(E, D, dtype=T, device=dev) if needs_shadow(prec) else None
         ops.gemm(prec, H1, Wb_t, bias=bb.detach(), z_out=Z2, act=ACT_SILU, out_f32=e0, out_t=e0_t)
         holder["e_t"] = e0_t if needs_shadow(prec) else e0
-        ctx.save_for_backward(feat, Z1, H1, Z2, Wb)
+        if need_bwd:
+            ctx.save_for_backward(feat, Z1, H1, Z2, Wb)
         ctx.prec, ctx.dim_edge = prec, dim_edge
         return e0
 
@@ -197,7 +199,8 @@ class _LayerFn(torch.autograd.Function):
         else:
             ops.gemm(prec, x_t, W1n_t, out_t=P)
         # per-edge first Linear with gathered projections, SiLU                       (cartnet.py:237,256)
-        Z = torch.empty(E, 2 * D, dtype=T, device=dev)
+        need_bwd = any(ctx.needs_input_grad)
+        Z = torch.empty(E, 2 * D, dtype=T, device=dev) if need_bwd else None     # inference: pre-activations are not stored
         H = torch.empty(E, 2 * D, dtype=T, device=dev)
         ops.gemm(prec, e_t, W1e_t, bias=b1.detach(), gather0=P[:, :2 * D], gidx0=plan.dst32,
                  gather1=P[:, 2 * D:], gidx1=plan.src32, z_out=Z, act=ACT_SILU, out_t=H)
@@ -225,7 +228,8 @@ class _LayerFn(torch.autograd.Function):
         x_out, x_out_t = ops.node_update(m, x, mean2, var2, w2.detach(), b2n.detach(), prec, True)   # cartnet.py:269,223
         cfg["holder"]["x_t"], cfg["holder"]["e_t"] = x_out_t, e_out_t
 
-        ctx.save_for_backward(x_t, e_t, Z, H, g, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
+        if need_bwd:
+            ctx.save_for_backward(x_t, e_t, Z, H, g, s, m, var1, mean2, var2, W1n, W1e, G2, A2, w1, b1n, w2, b2n)
         ctx.cfg = dict(prec=prec, plan=plan, dist=dist, training=training, radius=cfg["radius"],
                        use_envelope=cfg["use_envelope"], mean1=mean1)
         return x_out, e_out
@@ -336,10 +340,13 @@ class _NativeLayerFn(torch.autograd.Function):
         shadow = needs_shadow(prec)
         DD = D * D
         gn_t = None                                                  # no normalised copy: backward reads the centred g_t
-        tbuf = torch.empty(16 * DD + N * 4 * D + 2 * E * 2 * D + 2 * E * D, dtype=T, device=dev)
-        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, Z, H, s_t, g_t) = _carve(tbuf, [
-            (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D), (E, 2 * D),
-            (E, D), (E, D)])
+        need_bwd = any(ctx.needs_input_grad)                         # inference: the pre-activations Z are neither stored nor allocated
+        tbuf = torch.empty(16 * DD + N * 4 * D + (2 if need_bwd else 1) * E * 2 * D + 2 * E * D, dtype=T, device=dev)
+        (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, H, s_t, g_t, Z) = _carve(tbuf, [
+            (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D),
+            (E, D), (E, D), (E, 2 * D) if need_bwd else (0, 2 * D)])
+        if not need_bwd:
+            Z = None
         fbuf = torch.empty(N * D + 9 * D, dtype=torch.float32, device=dev)
         m, mean1, var1, mean2, var2, b1, center, bias_c, hsum = _carve(fbuf, [(N, D), (D,), (D,), (D,), (D,), (2 * D,), (D,), (D,), (D,)])
         x_out = torch.empty(N, D, dtype=torch.float32, device=dev)

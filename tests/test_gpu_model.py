@@ -315,3 +315,23 @@ def test_other_hidden_widths(dim_in, layers):
             scale = max(float(v.abs().max()) for v in ref["grads"].values())
             for k, g in ref["grads"].items():
                 assert float((got["grads"][k].cpu() - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-5 * scale, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+def test_inference_without_grad_is_bit_identical(precision):
+    """Under torch.no_grad() the forward pass neither allocates nor stores the pre-activations it would only need for a
+    backward pass (specialised GEMM epilogues without the z store): predictions must not change by a bit."""
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
+    batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
+    model = _model(kw, seed, lrad, precision).eval()
+    pa, _ = model(batch0.clone())
+    with torch.no_grad():
+        bb = batch0.clone()
+        pb, _ = model(bb)
+    assert torch.equal(pa.detach(), pb)
+    model.train()                                   # batch statistics, still no autograd graph
+    ref = _model(kw, seed, lrad, precision).train()
+    pc, _ = ref(batch0.clone())
+    with torch.no_grad():
+        pd, _ = model(batch0.clone())
+    assert torch.equal(pc.detach(), pd)
