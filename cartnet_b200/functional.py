@@ -271,7 +271,12 @@ class _LayerFn(torch.autograd.Function):
             dbg2 = w1.detach() * torch.rsqrt(var1 + ops.EPS_BN) * sums1[:D]
         # first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
         de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
-        ops.gemm(prec, dZ, _to_t(W1e.t(), prec), resid=de_out, out_f32=de_in)
+        W1eT = _to_t(W1e.t(), prec)
+        if prec == PREC_BF16X3:      # as in csrc/layer.cu: the gate and aggregate K halves as two launches with 128-row weight slices
+            for h in range(2):
+                ops.gemm(prec, dZ[:, h * D:(h + 1) * D], W1eT[:, h * D:(h + 1) * D], resid=de_out if h == 0 else de_in, out_f32=de_in)
+        else:
+            ops.gemm(prec, dZ, W1eT, resid=de_out, out_f32=de_in)
         dW1e = ops.gemm_tn(prec, dZ, e_t)
         # first Linear, node part: transpose of the two lifts = segmented sums by dst and by src
         dP = torch.empty(N, 4 * D, dtype=T, device=dev)

@@ -18,7 +18,7 @@ for name in common.MODEL_CASES:
     shape, sizes, seed, kw, lrad = common.MODEL_CASES[name]
     batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes), cholesky=kw["cholesky"],
                                         temperature=kw["temperature"]).to("cuda")
-    for precision in ("fp32", "tf32", "bf16"):
+    for precision in ("fp32", "bf16x3", "tf32", "bf16"):
         torch.manual_seed(0)
         model = cartnet_b200.CartNet(common.DIM_IN, common.DIM_RBF, common.NUM_LAYERS, radius=lrad, precision=precision, **kw)
         model.load_state_dict(fixtures.make_state_dict(model.state_dict(), seed))
@@ -44,5 +44,5 @@ for name in common.MODEL_CASES:
             r = common.rel_err(mine, ref)
             if r > worst:
                 worst, wk = r, k
-        print("%-16s %-5s train pred %.2e | eval pred %.2e | edge_attr %.2e | worst grad %.2e (%s)" % (
+        print("%-16s %-6s train pred %.2e | eval pred %.2e | edge_attr %.2e | worst grad %.2e (%s)" % (
             name, precision, e_pred, e_eval, e_e, worst, wk))
