@@ -205,3 +205,67 @@ def test_other_hidden_widths(dim_in, layers):
     got = common.run_train_step(model, batch_cpu.clone().to("cuda"))
     assert common.rel_err(got["pred"], ref["pred"]) < 2e-3
     assert common.rel_err(got["pred_eval"], ref["pred_eval"]) < 2e-3
+
+
+@pytest.mark.parametrize("temperature,atom_types", [(True, True), (False, True), (True, False), (False, False)])
+@pytest.mark.parametrize("cholesky", [True, False])
+def test_encoder_variants_and_heads(temperature, atom_types, cholesky):
+    """All four node-encoder variants (cartnet.py:144-154) with both heads in the default tensor-core mode: training step
+    against the oracle at 2e-3 (prediction, eval prediction, every gradient)."""
+    seed = 51
+    batch = fixtures.make_oracle_batch("mp", 5, seed, cholesky=cholesky, temperature=True)
+    if not cholesky:
+        batch.y = batch.y.reshape(-1)
+    kw = dict(invariant=False, temperature=temperature, use_envelope=True, atom_types=atom_types, cholesky=cholesky)
+    torch.manual_seed(0)
+    orc = O.OracleCartNet(256, 64, 2, **kw)
+    sd = fixtures.make_state_dict(orc.state_dict(), seed)
+    orc.load_state_dict(sd)
+    model = cartnet_b200.CartNet(256, 64, 2, precision="bf16x3", **kw)
+    model.load_state_dict(sd)
+    model.cuda()
+    ref = common.run_train_step(orc, batch)
+    got = common.run_train_step(model, batch.clone().to("cuda"))
+    assert common.rel_err(got["pred"], ref["pred"]) < 2e-3
+    assert common.rel_err(got["pred_eval"], ref["pred_eval"]) < 2e-3
+    scale = max(float(v.norm()) for v in ref["grads"].values())
+    for k, g in ref["grads"].items():
+        assert float((got["grads"][k].cpu() - g).abs().max()) <= 2e-3 * float(g.abs().max()) + 2e-3 * 5e-2 * scale, k
+
+
+def test_unsorted_edges_empty_graph_and_invariance():
+    """Edge cases in the default mode: an edge_index that is not dst-sorted (the layer sorts and un-sorts), a graph without
+    edges in eval mode, and -- with invariant=True -- independence of cart_dir (SURVEY.md §4 property 1), bit for bit."""
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["adp"]
+    batch0 = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
+    model = _model(kw, seed, lrad, "bf16x3").eval()
+    with torch.no_grad():
+        b1 = batch0.clone()
+        p1, _ = model(b1)
+        perm = torch.randperm(batch0.num_edges, generator=torch.Generator().manual_seed(1)).cuda()
+        b2 = batch0.clone()
+        b2.edge_index = b2.edge_index[:, perm].contiguous()
+        b2.cart_dist, b2.cart_dir = b2.cart_dist[perm], b2.cart_dir[perm]
+        p2, _ = model(b2)
+    # same kernels on the same edges; only the order inside a destination row (hence the fp32 summation order) differs
+    assert common.rel_err(p2, p1) < 1e-5 and common.rel_err(b2.edge_attr, b1.edge_attr[perm]) < 1e-5
+    from cartnet_b200.batch import CrystalBatch
+    fields = dict(x=torch.tensor([6, 8]), batch=torch.zeros(2, dtype=torch.int64), natoms=torch.tensor([2]),
+                  temperature=torch.tensor([0.3]), non_H_mask=torch.tensor([True, True]), y=torch.zeros(2, 3, 3),
+                  edge_index=torch.zeros(2, 0, dtype=torch.int64), cart_dist=torch.zeros(0), cart_dir=torch.zeros(0, 3))
+    orc = O.OracleCartNet(256, 64, 4, **kw)
+    orc.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    orc.eval()
+    with torch.no_grad():
+        pr, _ = orc(CrystalBatch(**fields))
+        pg, _ = model(CrystalBatch(**fields).to("cuda"))
+    assert common.rel_err(pg, pr) < 2e-3
+    shape, sizes, seed, kw, lrad = common.MODEL_CASES["invariant_noenv"]
+    bi = fixtures.make_oracle_batch(shape, len(sizes), seed, sizes=np.array(sizes)).to("cuda")
+    mi = _model(kw, seed, lrad, "bf16x3").eval()
+    with torch.no_grad():
+        pa, _ = mi(bi.clone())
+        bj = bi.clone()
+        bj.cart_dir = torch.randn_like(bj.cart_dir)
+        pb, _ = mi(bj)
+    assert torch.equal(pa, pb)
