@@ -1,6 +1,7 @@
 // Shared helpers for libcartnet_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -220,6 +221,32 @@ __device__ __forceinline__ void store4<bf16p_t>(bf16p_t* p, float4 v) {
     *reinterpret_cast<uint2*>(h) = hi;
     *reinterpret_cast<uint2*>(h + 128) = lo;
 }
+
+// ---- fp16 storage of pre-activations (CARTNET_PREC_BF16X3 only) ------------------------------------------------------
+// A pre-activation z is only ever re-read to evaluate silu'(z) in the backward pass. |d silu'(z)/dz * z| <= 0.25, so the
+// 2^-11 relative rounding of an fp16 word moves silu'(z) by at most 1.2e-4 (absolute, on a factor of order 1): far inside
+// the mode's 2e-3 budget, and half the bytes of the widest tensor a layer stores. Stores SATURATE (cvt.rn.satfinite), which
+// is exact for the purpose: silu' is 1 / 0 to fp32 precision long before |z| = 65504.
+struct half4raw { uint2 v; };
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // first source -> upper half
+    return r;
+}
+__device__ __forceinline__ float4 cvt_raw4(const half4raw& r) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> struct Raw4<__half> { using type = half4raw; };
+template <> __device__ __forceinline__ half4raw ld_raw4<__half>(const __half* p) { half4raw r; r.v = __ldg(reinterpret_cast<const uint2*>(p)); return r; }
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) { half4raw r; r.v = *reinterpret_cast<const uint2*>(p); return cvt_raw4(r); }
+template <> __device__ __forceinline__ float4 ldg4<__half>(const __half* p) { return cvt_raw4(ld_raw4<__half>(p)); }
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
+}
+// element type of the stored pre-activations (z_out / z_in of a GEMM epilogue, dsilu_mul): T, except fp16 in the pair mode
+template <typename T> struct ZOf { using type = T; };
+template <> struct ZOf<bf16p_t> { using type = __half; };
 
 // ---- activations (full-precision expf: the fp32 path is held to 1e-5) -------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }

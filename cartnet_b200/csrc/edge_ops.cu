@@ -223,9 +223,7 @@ struct SumF {
     __device__ void finish(int, double (*)[4]) const {}
 };
 // y = (T)(dy * silu'(z)) written on the fly, column sums of y (a bias gradient) as the reduction
-// z (a pre-activation) is only ever used elementwise: plain fp32 words in the bf16 pair mode (gemm_epilogue.cuh::GatherOf)
-template <typename T> struct ZOf { using type = T; };
-template <> struct ZOf<bf16p_t> { using type = float; };
+// z (a pre-activation) is only ever used elementwise: fp16 words in the bf16 pair mode (common.cuh::ZOf)
 
 template <typename T>
 struct DsiluMulF {

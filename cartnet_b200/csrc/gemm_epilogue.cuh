@@ -23,10 +23,10 @@ struct EpiParams {
     const typename GatherOf<T>::type* gather1;
     const int32_t* gidx1;
     int64_t ldg;
-    typename GatherOf<T>::type* z_out;
+    typename ZOf<T>::type* z_out;
     int64_t ldz;
     int act;
-    const typename GatherOf<T>::type* z_in;
+    const typename ZOf<T>::type* z_in;
     int64_t ldzin;
     const float* resid;
     int64_t ldr;
@@ -43,9 +43,9 @@ inline EpiParams<T> make_epi(const cartnet_gemm_t& d) {
     p.gather0 = (const typename GatherOf<T>::type*)d.gather0; p.gidx0 = d.gidx0;
     p.gather1 = (const typename GatherOf<T>::type*)d.gather1; p.gidx1 = d.gidx1;
     p.ldg = d.ldg;
-    p.z_out = (typename GatherOf<T>::type*)d.z_out; p.ldz = d.ldz;
+    p.z_out = (typename ZOf<T>::type*)d.z_out; p.ldz = d.ldz;
     p.act = d.act;
-    p.z_in = (const typename GatherOf<T>::type*)d.z_in; p.ldzin = d.ldzin;
+    p.z_in = (const typename ZOf<T>::type*)d.z_in; p.ldzin = d.ldzin;
     p.resid = d.resid; p.ldr = d.ldr;
     p.out_f32 = d.out_f32; p.ldo = d.ldo;
     p.out_t = (T*)d.out_t; p.ldt = d.ldt;

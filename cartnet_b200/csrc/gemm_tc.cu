@@ -211,6 +211,16 @@ template <> struct Raw8<__nv_bfloat16> { uint4 a; };
 template <> struct Raw8<tf32_t> { float4 a, b; };
 template <> struct Raw8<float> { float4 a, b; };
 template <> struct Raw8<bf16p_t> { uint4 hi, lo; };
+template <> struct Raw8<__half> { uint4 a; };
+__device__ __forceinline__ Raw8<__half> ld_raw8(const __half* p) { Raw8<__half> r; r.a = __ldg(reinterpret_cast<const uint4*>(p)); return r; }
+__device__ __forceinline__ void cvt_raw8(const Raw8<__half>& r, float4& v0, float4& v1) {
+    half4raw lo, hi;
+    lo.v = make_uint2(r.a.x, r.a.y); hi.v = make_uint2(r.a.z, r.a.w);
+    v0 = cvt_raw4(lo); v1 = cvt_raw4(hi);
+}
+__device__ __forceinline__ void store8(__half* p, const float4& v0, const float4& v1) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_half2_sat(v0.x, v0.y), pack_half2_sat(v0.z, v0.w), pack_half2_sat(v1.x, v1.y), pack_half2_sat(v1.z, v1.w));
+}
 __device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.a = __ldg(reinterpret_cast<const uint4*>(p)); return r; }
 __device__ __forceinline__ Raw8<tf32_t> ld_raw8(const tf32_t* p) {
     Raw8<tf32_t> r;
@@ -265,6 +275,20 @@ __device__ __forceinline__ void store8(bf16p_t* p, const float4& v0, const float
     *reinterpret_cast<uint4*>(h + 128) = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
+// CPT consecutive columns of one row (CPT = 4 or 8) as NV = CPT / 4 float4s, through the 4- or 8-element raw accessors.
+// Which CPT is best depends on the element size: a 32-column row segment of 4-byte elements is a full 128-byte line when 8
+// lanes own 4 columns each (one 16-byte access per lane), while 2-byte elements want 8 columns per lane.
+template <typename T, int CPT> struct RawV;
+template <typename T> struct RawV<T, 4> { typename Raw4<T>::type r; };
+template <typename T> struct RawV<T, 8> { Raw8<T> r; };
+template <typename T> __device__ __forceinline__ void ldv(RawV<T, 4>& o, const T* p) { o.r = ld_raw4<T>(p); }
+template <typename T> __device__ __forceinline__ void ldv(RawV<T, 8>& o, const T* p) { o.r = ld_raw8(p); }
+template <typename T> __device__ __forceinline__ void cvtv(const RawV<T, 4>& r, float4* v) { v[0] = cvt_raw4(r.r); }
+template <typename T> __device__ __forceinline__ void cvtv(const RawV<T, 8>& r, float4* v) { cvt_raw8(r.r, v[0], v[1]); }
+template <int CPT, typename T> __device__ __forceinline__ void storev(T* p, const float4* v) {
+    if (CPT == 4) store4<T>(p, v[0]); else store8(p, v[0], v[1]);
+}
+
 // the arithmetic of the epilogue on 4 consecutive columns of one row (no stores): v = acc + bias + gathers; zval = v;
 // v = act(v, z_in); v += resid
 template <typename T, int EPI>
@@ -283,19 +307,22 @@ __device__ __forceinline__ void epi_math4(const EpiParams<T>& p, float4& v, floa
     if (epi_has<EPI>(EB_RESID, p.resid != nullptr)) { v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w; }
 }
 
-// The 8 row groups of a warp (lane >> 2) hold partial column sums of the same 8 columns: combine them with a fixed
-// butterfly, then the owner lane (lane < 4) adds the 32-row block sums to the warp's running totals in shared memory.
-__device__ __forceinline__ void stats_flush8(float* wstat, int cidx, int lane, float4* ss, float4* sq) {
+// The 32 / LPR row groups of a warp hold partial column sums of the same CPT columns: combine them with a fixed butterfly
+// (lanes that differ only in the row-group bits), then the owner lanes (row group 0) add the 32-row block sums to the warp's
+// running totals in shared memory.
+template <int CPT>
+__device__ __forceinline__ void stats_flushv(float* wstat, int cidx, int lane, float4* ss, float4* sq) {
+    constexpr int NV = CPT / 4, LPR = 32 / CPT;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NV; ++h) {
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
+        for (int o = LPR; o <= 16; o <<= 1) {
             ss[h].x += __shfl_xor_sync(0xffffffffu, ss[h].x, o); ss[h].y += __shfl_xor_sync(0xffffffffu, ss[h].y, o);
             ss[h].z += __shfl_xor_sync(0xffffffffu, ss[h].z, o); ss[h].w += __shfl_xor_sync(0xffffffffu, ss[h].w, o);
             sq[h].x += __shfl_xor_sync(0xffffffffu, sq[h].x, o); sq[h].y += __shfl_xor_sync(0xffffffffu, sq[h].y, o);
             sq[h].z += __shfl_xor_sync(0xffffffffu, sq[h].z, o); sq[h].w += __shfl_xor_sync(0xffffffffu, sq[h].w, o);
         }
-        if (lane < 4) {
+        if (lane < LPR) {
             float4* a = reinterpret_cast<float4*>(wstat + cidx + 4 * h);
             float4* b = reinterpret_cast<float4*>(wstat + 128 + cidx + 4 * h);
             float4 va = *a, vb = *b;
@@ -436,7 +463,20 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c_begin = grp * cols_per_grp;
         const int c_end = (c_begin + cols_per_grp) < BN ? (c_begin + cols_per_grp) : BN;
         float* stg = smemStg + (warp - 2) * 32 * NT_STG_PITCH;
-        const int sub_r = lane >> 2, sub_c = (lane & 3) * 8;       // 8 row groups x 4 column groups of 8 columns
+        // columns per thread. Measured on the ADP-64 shapes (same box, scripts/gemm_microbench.py): 8 columns win wherever the
+        // epilogue reads row-gathered or pre-activation tensors (GEMM1 pair mode 0.925 vs 1.07 ms: one full 32-byte sector per
+        // lane and half the load instructions) and for 2-byte operands; 4 columns (a full 128-byte line per row and
+        // instruction) win by ~3 % for the store-only / residual epilogues of the 4-byte modes.
+#ifdef CN_NT_CPT_FORCE
+        constexpr int CPT = CN_NT_CPT_FORCE;        // A/B builds only
+#else
+        constexpr int CPT = (sizeof(T) == 2 || EPI < 0 || (EPI & (EB_GATHER | EB_DSILU)) != 0) ? 8 : 4;
+#endif
+        constexpr int NV = CPT / 4;                 // float4s per thread and row
+        constexpr int LPR = 32 / CPT;               // lanes per 32-column row segment
+        constexpr int RPI = 32 / LPR;               // rows per instruction
+        constexpr int NIT = 32 / RPI;               // row iterations per 32-row block
+        const int sub_r = lane / LPR, sub_c = (lane % LPR) * CPT;
         // EB_STATS: this warp's running column sums over all of its tiles (fp32; the caller centres the output so that
         // |mean| <~ std), one owner lane per column -> fixed order, no atomics; written out as fp64 partials at the end
         float* wstat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(NtBars) + 15) & ~(size_t)15)) + (warp - 2) * 256;
@@ -445,11 +485,11 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // 32-column blocks per warp), so each thread keeps the running sums of its 8 columns in registers over ALL its
         // tiles; the 8 row groups are combined once, at the end, by the same fixed butterfly
         constexpr bool kStatsRegs = kStats && TR::NP == 2;
-        float4 rs_s[2][2], rs_q[2][2];
+        float4 rs_s[2][NV], rs_q[2][NV];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) rs_s[a][h] = rs_q[a][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int h = 0; h < NV; ++h) rs_s[a][h] = rs_q[a][h] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kStats && !kStatsRegs) {
             for (int i = lane; i < 256; i += 32) wstat[i] = 0.f;
             __syncwarp();
@@ -458,25 +498,23 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles && c_begin < c_end; mt += m_stride) {
             const int64_t row0 = (int64_t)mt * 128 + q * 32;
-            // gather-row indices of the 4 output rows this thread finishes (hoisted out of the column loop)
-            int32_t i0[4], i1[4];
+            // gather-row indices of the warp's 32 output rows, one row per lane (hoisted out of the column loop); the thread
+            // that finishes row it * RPI + sub_r fetches its index with a shuffle
+            int32_t i0v = 0, i1v = 0;
             if (epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr)) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t row = row0 + it * 8 + sub_r;
-                    i0[it] = row < M ? epi.gidx0[row] : 0;
-                    i1[it] = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
-                }
+                const int64_t row = row0 + lane;
+                i0v = row < M ? epi.gidx0[row] : 0;
+                i1v = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
             }
             const bool full = row0 + 32 <= (int64_t)M;
             bool first = true;
             for (int c = c_begin; c < c_end; c += 32) {
                 const int col = n0 + c + sub_c;
-                float4 bias0 = make_float4(0.f, 0.f, 0.f, 0.f), bias1 = bias0;
-                if (epi_has<EPI>(EB_BIAS, epi.bias != nullptr)) {
-                    bias0 = *reinterpret_cast<const float4*>(epi.bias + col);
-                    bias1 = *reinterpret_cast<const float4*>(epi.bias + col + 4);
-                }
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 bias[NV];
+#pragma unroll
+                for (int h = 0; h < NV; ++h)
+                    bias[h] = epi_has<EPI>(EB_BIAS, epi.bias != nullptr) ? *reinterpret_cast<const float4*>(epi.bias + col + 4 * h) : zero;
                 const bool has_g0 = epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr);
                 const bool has_g1 = epi_has<EPI>(EB_GATHER, epi.gather1 != nullptr);
                 const bool has_z = epi_has<EPI>(EB_DSILU, epi.act == CARTNET_ACT_MUL_DSILU);
@@ -484,23 +522,26 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 // phase 1: every global read of this 32x32 block is issued up front -- before the accumulator is even
                 // fetched from TMEM, so that their L2 / HBM round trip overlaps the tcgen05.ld + shared-memory transpose
                 // (and, for a tile's first block, the wait for its MMAs) -- and before any store, whose possible aliasing
-                // would otherwise serialise the round trips. A thread owns 8 consecutive columns of 4 rows: every global
-                // access is a 16-byte vector (4 lanes cover a 32-column row segment, 8 rows per instruction).
+                // would otherwise serialise the round trips. A thread owns CPT consecutive columns of NIT rows; every
+                // global access is a 16-byte (or, for pair halves at CPT = 4, 8-byte) vector.
                 // FULL blocks (all 32 rows < M, i.e. every block but the last few) carry no per-row predicates so the
                 // compiler can interleave the independent rows and hide the MUFU / FMA latencies.
-                Raw8<typename GatherOf<T>::type> ra[4], rb[4], rz[4];
-                float4 rr[4][2];
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                using G = typename GatherOf<T>::type;
+                RawV<G, CPT> ra[NIT], rb[NIT];
+                RawV<typename ZOf<T>::type, CPT> rz[NIT];
+                float4 rr[NIT][NV];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t row = row0 + it * 8 + sub_r;
+                for (int it = 0; it < NIT; ++it) {
+                    const int64_t row = row0 + it * RPI + sub_r;
+                    const int32_t i0 = has_g0 ? __shfl_sync(0xffffffffu, i0v, it * RPI + sub_r) : 0;
+                    const int32_t i1 = has_g1 ? __shfl_sync(0xffffffffu, i1v, it * RPI + sub_r) : 0;
                     if (full || row < M) {
-                        if (has_g0) ra[it] = ld_raw8(epi.gather0 + (int64_t)i0[it] * epi.ldg + col);
-                        if (has_g1) rb[it] = ld_raw8(epi.gather1 + (int64_t)i1[it] * epi.ldg + col);
-                        if (has_z) rz[it] = ld_raw8(epi.z_in + row * epi.ldzin + col);
+                        if (has_g0) ldv(ra[it], epi.gather0 + (int64_t)i0 * epi.ldg + col);
+                        if (has_g1) ldv(rb[it], epi.gather1 + (int64_t)i1 * epi.ldg + col);
+                        if (has_z) ldv(rz[it], epi.z_in + row * epi.ldzin + col);
                         if (has_r) {
-                            rr[it][0] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col));
-                            rr[it][1] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col + 4));
+#pragma unroll
+                            for (int h = 0; h < NV; ++h) rr[it][h] = __ldg(reinterpret_cast<const float4*>(epi.resid + row * epi.ldr + col + 4 * h));
                         }
                     }
                 }
@@ -515,38 +556,46 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * NT_STG_PITCH + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                float4 t8[4][2];
+                float4 tv[NIT][NV];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int srow = it * 8 + sub_r;
+                for (int it = 0; it < NIT; ++it) {
+                    const int srow = it * RPI + sub_r;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        t8[it][h] = *reinterpret_cast<const float4*>(stg + srow * NT_STG_PITCH + 4 * (((sub_c >> 2) + h) ^ (srow & 7)));
+                    for (int h = 0; h < NV; ++h)
+                        tv[it][h] = *reinterpret_cast<const float4*>(stg + srow * NT_STG_PITCH + 4 * (((sub_c >> 2) + h) ^ (srow & 7)));
                 }
                 __syncwarp();
-                float4 ss[2] = {zero, zero}, sq[2] = {zero, zero};
+                float4 ss[NV], sq[NV];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t row = row0 + it * 8 + sub_r;
+                for (int h = 0; h < NV; ++h) ss[h] = sq[h] = zero;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int64_t row = row0 + it * RPI + sub_r;
                     if (full || row < M) {
-                        float4 ga0 = zero, ga1 = zero, gb0 = zero, gb1 = zero, z0 = zero, z1 = zero, zv0, zv1;
-                        if (has_g0) cvt_raw8(ra[it], ga0, ga1);
-                        if (has_g1) cvt_raw8(rb[it], gb0, gb1);
-                        if (has_z) cvt_raw8(rz[it], z0, z1);
-                        float4 o0 = t8[it][0], o1 = t8[it][1];
-                        epi_math4<T, EPI>(epi, o0, zv0, bias0, has_g0, has_g1, ga0, gb0, z0, has_r ? rr[it][0] : zero);
-                        epi_math4<T, EPI>(epi, o1, zv1, bias1, has_g0, has_g1, ga1, gb1, z1, has_r ? rr[it][1] : zero);
-                        if (epi_has<EPI>(EB_ZOUT, epi.z_out != nullptr)) store8(epi.z_out + row * epi.ldz + col, zv0, zv1);
-                        if (epi_has<EPI>(EB_OUTF, epi.out_f32 != nullptr)) {
-                            *reinterpret_cast<float4*>(epi.out_f32 + row * epi.ldo + col) = o0;
-                            *reinterpret_cast<float4*>(epi.out_f32 + row * epi.ldo + col + 4) = o1;
+                        float4 ga[NV], gb[NV], zi[NV], zv[NV], o[NV];
+#pragma unroll
+                        for (int h = 0; h < NV; ++h) ga[h] = gb[h] = zi[h] = zero;
+                        if (has_g0) cvtv(ra[it], ga);
+                        if (has_g1) cvtv(rb[it], gb);
+                        if (has_z) cvtv(rz[it], zi);
+#pragma unroll
+                        for (int h = 0; h < NV; ++h) {
+                            o[h] = tv[it][h];
+                            epi_math4<T, EPI>(epi, o[h], zv[h], bias[h], has_g0, has_g1, ga[h], gb[h], zi[h], has_r ? rr[it][h] : zero);
                         }
-                        if (epi_has<EPI>(EB_OUTT, epi.out_t != nullptr)) store8(epi.out_t + row * epi.ldt + col, o0, o1);
+                        if (epi_has<EPI>(EB_ZOUT, epi.z_out != nullptr)) storev<CPT>(epi.z_out + row * epi.ldz + col, zv);
+                        if (epi_has<EPI>(EB_OUTF, epi.out_f32 != nullptr)) {
+#pragma unroll
+                            for (int h = 0; h < NV; ++h) *reinterpret_cast<float4*>(epi.out_f32 + row * epi.ldo + col + 4 * h) = o[h];
+                        }
+                        if (epi_has<EPI>(EB_OUTT, epi.out_t != nullptr)) storev<CPT>(epi.out_t + row * epi.ldt + col, o);
                         if (kStats) {
-                            ss[0].x += o0.x; ss[0].y += o0.y; ss[0].z += o0.z; ss[0].w += o0.w;
-                            ss[1].x += o1.x; ss[1].y += o1.y; ss[1].z += o1.z; ss[1].w += o1.w;
-                            sq[0].x = fmaf(o0.x, o0.x, sq[0].x); sq[0].y = fmaf(o0.y, o0.y, sq[0].y); sq[0].z = fmaf(o0.z, o0.z, sq[0].z); sq[0].w = fmaf(o0.w, o0.w, sq[0].w);
-                            sq[1].x = fmaf(o1.x, o1.x, sq[1].x); sq[1].y = fmaf(o1.y, o1.y, sq[1].y); sq[1].z = fmaf(o1.z, o1.z, sq[1].z); sq[1].w = fmaf(o1.w, o1.w, sq[1].w);
+#pragma unroll
+                            for (int h = 0; h < NV; ++h) {
+                                ss[h].x += o[h].x; ss[h].y += o[h].y; ss[h].z += o[h].z; ss[h].w += o[h].w;
+                                sq[h].x = fmaf(o[h].x, o[h].x, sq[h].x); sq[h].y = fmaf(o[h].y, o[h].y, sq[h].y);
+                                sq[h].z = fmaf(o[h].z, o[h].z, sq[h].z); sq[h].w = fmaf(o[h].w, o[h].w, sq[h].w);
+                            }
                         }
                     }
                 }
@@ -556,13 +605,13 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int a = 0; a < 2; ++a)
                         if (a == cb) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
+                            for (int h = 0; h < NV; ++h) {
                                 rs_s[a][h].x += ss[h].x; rs_s[a][h].y += ss[h].y; rs_s[a][h].z += ss[h].z; rs_s[a][h].w += ss[h].w;
                                 rs_q[a][h].x += sq[h].x; rs_q[a][h].y += sq[h].y; rs_q[a][h].z += sq[h].z; rs_q[a][h].w += sq[h].w;
                             }
                         }
                 } else if (kStats) {
-                    stats_flush8(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
+                    stats_flushv<CPT>(wstat, c - c_begin + sub_c, lane, ss, sq);      // rows >= M contribute nothing
                 }
             }
             tc_fence_before();
@@ -577,15 +626,15 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int a = 0; a < 2; ++a) {
                 if (c_begin + 32 * a >= c_end) break;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < NV; ++h) {
 #pragma unroll
-                    for (int o = 4; o <= 16; o <<= 1) {
+                    for (int o = LPR; o <= 16; o <<= 1) {
                         rs_s[a][h].x += __shfl_xor_sync(0xffffffffu, rs_s[a][h].x, o); rs_s[a][h].y += __shfl_xor_sync(0xffffffffu, rs_s[a][h].y, o);
                         rs_s[a][h].z += __shfl_xor_sync(0xffffffffu, rs_s[a][h].z, o); rs_s[a][h].w += __shfl_xor_sync(0xffffffffu, rs_s[a][h].w, o);
                         rs_q[a][h].x += __shfl_xor_sync(0xffffffffu, rs_q[a][h].x, o); rs_q[a][h].y += __shfl_xor_sync(0xffffffffu, rs_q[a][h].y, o);
                         rs_q[a][h].z += __shfl_xor_sync(0xffffffffu, rs_q[a][h].z, o); rs_q[a][h].w += __shfl_xor_sync(0xffffffffu, rs_q[a][h].w, o);
                     }
-                    if (lane < 4) {
+                    if (lane < LPR) {
                         const int64_t cg = n0 + c_begin + 32 * a + sub_c + 4 * h;
                         double* ps = stats + (blk * 2 + 0) * N + cg;
                         double* pq = stats + (blk * 2 + 1) * N + cg;

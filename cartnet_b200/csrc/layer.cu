@@ -57,6 +57,7 @@ __global__ void bias_grad_kernel(const float* __restrict__ sums1, const float* _
 }
 
 static inline size_t tsize(int prec) { return prec == CARTNET_PREC_BF16 ? 2 : 4; }
+static inline size_t zsize(int prec) { return prec == CARTNET_PREC_BF16X3 ? 2 : tsize(prec); }   // pre-activations: fp16 in the pair mode
 static inline const void* toff(const void* p, int prec, int64_t elems) { return (const char*)p + elems * (int64_t)tsize(prec); }
 static inline void* toff(void* p, int prec, int64_t elems) { return (char*)p + elems * (int64_t)tsize(prec); }
 
@@ -180,7 +181,7 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
         d.act = CARTNET_ACT_MUL_DSILU; d.z_in = L->Z; d.ldzin = 2 * D; d.out_t = L->dZ; d.ldt = 2 * D;
         CN_TRY(cartnet_gemm(&d, st));
         cartnet_gemm_t a = gemm_desc(prec, (int)E, D, D, L->ds_t, D, L->A2T_t, D);
-        a.act = CARTNET_ACT_MUL_DSILU; a.z_in = toff((const void*)L->Z, prec, D); a.ldzin = 2 * D;
+        a.act = CARTNET_ACT_MUL_DSILU; a.z_in = (const char*)L->Z + (int64_t)D * (int64_t)zsize(prec); a.ldzin = 2 * D;
         a.out_t = toff(L->dZ, prec, D); a.ldt = 2 * D;
         CN_TRY(cartnet_gemm(&a, st));
     }

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype
+from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype, z_dtype
 
 
 def _round_up(v: int, m: int) -> int:
@@ -45,10 +45,10 @@ class _EdgeEncoderFn(torch.autograd.Function):
         Wa_t = _to_t(F.pad(Wa.detach(), (0, KF - dim_edge)), prec)
         Wb_t = _to_t(Wb, prec)
         need_bwd = any(ctx.needs_input_grad)       # inference (torch.no_grad): the pre-activations are never read -- not stored
-        Z1 = torch.empty(E, D2, dtype=T, device=dev) if need_bwd else None
+        Z1 = torch.empty(E, D2, dtype=z_dtype(prec), device=dev) if need_bwd else None
         H1 = torch.empty(E, D2, dtype=T, device=dev)
         ops.gemm(prec, feat, Wa_t, bias=ba.detach(), z_out=Z1, act=ACT_SILU, out_t=H1)
-        Z2 = torch.empty(E, D, dtype=T, device=dev) if need_bwd else None
+        Z2 = torch.empty(E, D, dtype=z_dtype(prec), device=dev) if need_bwd else None
         e0 = torch.empty(E, D, dtype=torch.float32, device=dev)
         e0_t = torch.empty(E, D, dtype=T, device=dev) if needs_shadow(prec) else None
         ops.gemm(prec, H1, Wb_t, bias=bb.detach(), z_out=Z2, act=ACT_SILU, out_f32=e0, out_t=e0_t)
@@ -65,7 +65,7 @@ class _EdgeEncoderFn(torch.autograd.Function):
         T = t_dtype(prec)
         dz2, dbb = ops.dsilu_mul(de0.contiguous(), Z2, prec, want_colsum=True)     # [E, D]; sum_e dz2 from the same pass
         dWb = ops.gemm_tn(prec, dz2, H1)                                # [D, 2D]
-        dz1 = torch.empty_like(Z1)
+        dz1 = torch.empty(Z1.shape, dtype=T, device=Z1.device)
         ops.gemm(prec, dz2, _to_t(Wb.t(), prec), act=ACT_MUL_DSILU, z_in=Z1, out_t=dz1)
         dWa_full = ops.gemm_tn(prec, dz1, feat)                         # [2D, KF]
         dWa = dWa_full[:, :ctx.dim_edge]
@@ -94,7 +94,7 @@ class _LinearSiluFn(torch.autograd.Function):
         gp = PREC_TF32 if prec == PREC_BF16 else prec
         M, N = int(x.shape[0]), int(W.shape[0])
         x_t = ops.cast(x.detach().contiguous(), gp)
-        Z = torch.empty(M, N, dtype=t_dtype(gp), device=x.device)
+        Z = torch.empty(M, N, dtype=z_dtype(gp), device=x.device)
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
         ops.gemm(gp, x_t, _to_t(W, gp), bias=b.detach(), z_out=Z, act=ACT_SILU, out_f32=y)
         ctx.save_for_backward(x_t, Z, W)
@@ -200,7 +200,7 @@ class _LayerFn(torch.autograd.Function):
             ops.gemm(prec, x_t, W1n_t, out_t=P)
         # per-edge first Linear with gathered projections, SiLU                       (cartnet.py:237,256)
         need_bwd = any(ctx.needs_input_grad)
-        Z = torch.empty(E, 2 * D, dtype=T, device=dev) if need_bwd else None     # inference: pre-activations are not stored
+        Z = torch.empty(E, 2 * D, dtype=z_dtype(prec), device=dev) if need_bwd else None     # inference: pre-activations are not stored
         H = torch.empty(E, 2 * D, dtype=T, device=dev)
         ops.gemm(prec, e_t, W1e_t, bias=b1.detach(), gather0=P[:, :2 * D], gidx0=plan.dst32,
                  gather1=P[:, 2 * D:], gidx1=plan.src32, z_out=Z, act=ACT_SILU, out_t=H)
@@ -346,12 +346,12 @@ class _NativeLayerFn(torch.autograd.Function):
         DD = D * D
         gn_t = None                                                  # no normalised copy: backward reads the centred g_t
         need_bwd = any(ctx.needs_input_grad)                         # inference: the pre-activations Z are neither stored nor allocated
-        tbuf = torch.empty(16 * DD + N * 4 * D + (2 if need_bwd else 1) * E * 2 * D + 2 * E * D, dtype=T, device=dev)
+        zw = 2 * D * z_dtype(prec).itemsize // T.itemsize            # width of a Z row in T words (fp16 Z in the pair mode)
+        tbuf = torch.empty(16 * DD + N * 4 * D + E * 2 * D + (E * zw if need_bwd else 0) + 2 * E * D, dtype=T, device=dev)
         (W1n_t, W1e_t, G2_t, A2_t, W1nT_t, W1eT_t, G2T_t, A2T_t, P, H, s_t, g_t, Z) = _carve(tbuf, [
             (4 * D, D), (2 * D, D), (D, D), (D, D), (D, 4 * D), (D, 2 * D), (D, D), (D, D), (N, 4 * D), (E, 2 * D),
-            (E, D), (E, D), (E, 2 * D) if need_bwd else (0, 2 * D)])
-        if not need_bwd:
-            Z = None
+            (E, D), (E, D), (E, zw) if need_bwd else (0, zw)])
+        Z = Z.view(z_dtype(prec)) if need_bwd else None
         fbuf = torch.empty(N * D + 9 * D, dtype=torch.float32, device=dev)
         m, mean1, var1, mean2, var2, b1, center, bias_c, hsum = _carve(fbuf, [(N, D), (D,), (D,), (D,), (D,), (2 * D,), (D,), (D,), (D,)])
         x_out = torch.empty(N, D, dtype=torch.float32, device=dev)

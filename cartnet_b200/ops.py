@@ -27,6 +27,13 @@ def t_dtype(prec: int) -> torch.dtype:
     return torch.bfloat16 if prec == PREC_BF16 else torch.float32
 
 
+def z_dtype(prec: int) -> torch.dtype:
+    """torch dtype of stored pre-activations (`z_out` / `z_in` of `gemm`, `z` of `dsilu_mul`): the operand dtype, except
+    fp16 in PREC_BF16X3 -- a pre-activation is only re-read to evaluate silu'(z), which 2^-11 relative rounding moves by
+    at most 1.2e-4 (csrc/common.cuh::ZOf); stores saturate."""
+    return torch.float16 if prec == PREC_BF16X3 else t_dtype(prec)
+
+
 def f32_storage(prec: int) -> bool:
     """dtype of T-typed buffers is torch.float32 (fp32 and tf32 modes)"""
     return prec != PREC_BF16
@@ -255,10 +262,10 @@ def gemm(prec: int, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, 
             raise ValueError("gemm: gather0/gather1 must share a leading dimension")
         d.gather1, d.gidx1, d.ldg = _p(gather1), _p(gidx1), _ld2(gather1)
     if z_out is not None:
-        _req(z_out, T, "z_out"); d.z_out, d.ldz = _p(z_out), _ld2(z_out)
+        _req(z_out, z_dtype(prec), "z_out"); d.z_out, d.ldz = _p(z_out), _ld2(z_out)
     d.act = act
     if z_in is not None:
-        _req(z_in, T, "z_in"); d.z_in, d.ldzin = _p(z_in), _ld2(z_in)
+        _req(z_in, z_dtype(prec), "z_in"); d.z_in, d.ldzin = _p(z_in), _ld2(z_in)
     if resid is not None:
         _req(resid, torch.float32, "resid"); d.resid, d.ldr = _p(resid), _ld2(resid)
     if out_f32 is not None:
@@ -472,7 +479,7 @@ def segment_sum_pair(x, row_ptr, col_ptr, perm_src, num_nodes: int, out, prec: i
 def dsilu_mul(dy, z, prec: int, want_colsum: bool = False):
     """y = (T)(dy * silu'(z)); with want_colsum also the column sums of y (fp32 [C]) from the same pass."""
     lib = _lib.load()
-    _req(dy, torch.float32, "dy"); _req(z, t_dtype(prec), "z")
+    _req(dy, torch.float32, "dy"); _req(z, z_dtype(prec), "z")
     rows, Cc = int(z.shape[0]), int(z.shape[1])
     y = torch.empty(rows, Cc, dtype=t_dtype(prec), device=z.device)
     tpr = Cc // 4

@@ -21,6 +21,8 @@
  *                       (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM). Bases must be 256-byte aligned, row pitches
  *                       and column offsets multiples of 64 elements. This is the tensor-core mode that holds the 2e-3
  *                       tolerance in TRAINING mode (edge BatchNorm amplifies operand rounding ~15x).
+ *                       Tensors that are never contracted are NOT pair-typed in this mode: gathered addends are plain
+ *                       fp32, stored pre-activations (z_out / z_in / dsilu_mul's z) are fp16 with saturating stores.
  */
 #ifndef CARTNET_B200_H
 #define CARTNET_B200_H
@@ -158,11 +160,11 @@ typedef struct cartnet_gemm {
     const void* gather1;     /* v += gather1[gidx1[row]*ldg + col]      (T) */
     const int32_t* gidx1;
     int64_t ldg;
-    void* z_out;             /* z_out[row*ldz + col] = v                (T; plain fp32 in the BF16X3 mode, like gather*) */
+    void* z_out;             /* z_out[row*ldz + col] = v                (T; fp16 words, saturating, in the BF16X3 mode) */
     int64_t ldz;
     int32_t act;             /* CARTNET_ACT_*: none | v = silu(v) | v *= silu'(z_in[row*ldzin+col]) */
     int32_t _pad;
-    const void* z_in;        /* T (plain fp32 in the BF16X3 mode) */
+    const void* z_in;        /* T (fp16 in the BF16X3 mode) */
     int64_t ldzin;
     const float* resid;      /* v += resid[row*ldr + col] */
     int64_t ldr;
@@ -339,7 +341,7 @@ typedef struct cartnet_layer {
     void *W1n_t, *W1e_t, *G2_t, *A2_t, *W1nT_t, *W1eT_t, *G2T_t, *A2T_t;
     float* b1;
     /* forward: saved activations and outputs */
-    void *P, *Z, *H;                                 /* T: [N,4D], [E,2D], [E,2D] */
+    void *P, *Z, *H;                                 /* T: [N,4D], [E,2D], [E,2D]; BF16X3: P plain fp32, Z fp16 */
     void* g_t;                                       /* T [E,D]: centred gate pre-activation (scratch after the forward pass) */
     float *center, *bias_c, *hsum;                   /* [D] each: cartnet_gate_center outputs / scratch */
     float* m;                                        /* [N,D] */

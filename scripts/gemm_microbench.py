@@ -52,13 +52,13 @@ def nt(M, Nn, K, mode):
         elif mode == "gather_silu_local":   # src close to dst (sorted): L1-friendly
             src = dst.clone()
         kw = dict(bias=torch.randn(Nn, device=dev), gather0=P[:, :Nn], gidx0=dst, gather1=P[:, Nn:], gidx1=src,
-                  z_out=torch.empty(M, Nn, device=dev, dtype=T), act=ops.ACT_SILU, out_t=torch.empty(M, Nn, device=dev, dtype=T))
+                  z_out=torch.empty(M, Nn, device=dev, dtype=ops.z_dtype(prec)), act=ops.ACT_SILU, out_t=torch.empty(M, Nn, device=dev, dtype=T))
     elif mode == "resid":
         kw = dict(resid=torch.randn(M, Nn, device=dev), out_f32=torch.empty(M, Nn, device=dev))
     elif mode == "bias_tout":
         kw = dict(bias=torch.randn(Nn, device=dev), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     elif mode == "dsilu":
-        kw = dict(act=ops.ACT_MUL_DSILU, z_in=(torch.randn(M, Nn, device=dev) if prec == ops.PREC_BF16X3 else tt(torch.randn(M, Nn, device=dev))), out_t=torch.empty(M, Nn, device=dev, dtype=T))
+        kw = dict(act=ops.ACT_MUL_DSILU, z_in=(torch.randn(M, Nn, device=dev).half() if prec == ops.PREC_BF16X3 else tt(torch.randn(M, Nn, device=dev))), out_t=torch.empty(M, Nn, device=dev, dtype=T))
     ms = timeit(lambda: ops.gemm(prec, A, B, **kw), reps)
     print("NT  M=%7d N=%4d K=%4d %-12s %8.3f ms  %7.1f TFLOP/s" % (M, Nn, K, mode, ms, 2.0 * M * Nn * K / ms / 1e9))
 

@@ -112,8 +112,8 @@ def gemm(prec, A, B, *, bias=None, gather0=None, gidx0=None, gather1=None, gidx1
         v = v + _f(gather0)[gidx0.long()]
     if gather1 is not None:
         v = v + _f(gather1)[gidx1.long()]
-    if z_out is not None:      # pre-activations are only used elementwise: plain fp32 in the pair mode
-        z_out.copy_(v.to(torch.float32) if prec == PREC_BF16X3 else _shadow(v, prec))
+    if z_out is not None:      # pre-activations are only used elementwise: fp16 words in the pair mode (the copy rounds)
+        z_out.copy_(v.to(torch.float32).clamp(-65504.0, 65504.0) if prec == PREC_BF16X3 else _shadow(v, prec))
     if act == ACT_SILU:
         v = F.silu(v)
     elif act == ACT_MUL_DSILU:

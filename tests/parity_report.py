@@ -42,7 +42,7 @@ for name in common.MODEL_CASES:
             if float(ref.abs().max()) < 1e-4 * max(float(gm[pre + "gradnorm/" + q]) for q in gk):
                 continue
             r = common.rel_err(mine, ref)
-            if r > worst:
+            if not (r <= worst):      # NaN must surface as the worst entry
                 worst, wk = r, k
         print("%-16s %-6s train pred %.2e | eval pred %.2e | edge_attr %.2e | worst grad %.2e (%s)" % (
             name, precision, e_pred, e_eval, e_e, worst, wk))
