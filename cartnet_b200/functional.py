@@ -335,6 +335,10 @@ class _NativeLayerFn(torch.autograd.Function):
             raise RuntimeError("cartnet_b200: CartNet_layer needs CUDA tensors (no CPU fallback exists)")
         N, D = int(x.shape[0]), int(x.shape[1])
         E = int(e.shape[0])
+        # Backward reads x, e and the parameters through raw pointers (ctx.L): saving the autograd-visible tensors as well
+        # costs nothing (same storage) and keeps autograd's version check -- an in-place update of any of them between
+        # forward and backward raises the standard error instead of silently producing gradients of the new values
+        ctx.save_for_backward(x, e, G1, A1, bg1, ba1, G2, A2, bg2, ba2, w1, b1n, w2, b2n)
         x = x.detach().contiguous()
         e = e.detach().contiguous()
         x_t, e_t = cfg.get("x_t"), cfg.get("e_t")
@@ -397,6 +401,7 @@ class _NativeLayerFn(torch.autograd.Function):
         if ctx.keep is None:
             raise RuntimeError("cartnet_b200: CartNet_layer backward was called a second time, but its saved activations "
                                "have already been freed (run the forward pass again; retain_graph is not supported)")
+        ctx.saved_tensors      # noqa: B018 -- version check of x, e and the parameters (see forward)
         L = ctx.L
         N, E, D, prec = ctx.dims
         T = t_dtype(prec)
