@@ -671,6 +671,67 @@ segment_sum_pair_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __r
     }
 }
 
+// Same result set as segment_sum_pair_kernel, laid out for L2 reuse. Every row of x is wanted twice (once through each CSR)
+// and both uses belong to nodes of the same crystal, but with one thread column per (node, 4 columns) ~2 400 nodes are in
+// flight at once: ~12 ADP crystals x 43 MB of rows (4-byte operands, C = 512) against 126 MB of L2, and the second read of
+// a row went back to HBM (ncu: 2.66 GB read per launch for a 1.41 GB tensor). Here RL row lanes share a node (lane q adds
+// rows q, q + RL, ... of the segment in order, the RL partial sums are combined in lane order: still one fixed order), so
+// the same number of loads is in flight with RL x fewer nodes -- ~300 nodes = 1.5 crystals -- and the second read hits L2:
+// ncu 1.44 GB of DRAM reads per launch instead of 2.75. The launch itself is only 5 % shorter (397 vs 419 us): L2 -> SM
+// delivery (~7 TB/s here) is no faster than HBM, so on this part L2 reuse saves DRAM traffic, not time.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(1024, 2)
+segment_sum_pair_lanes_kernel(const T* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_ptr,
+                              const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ perm, int num_nodes, int C,
+                              int RL, TO* __restrict__ out, int64_t ldo) {
+    constexpr int U = 2;                                     // rows of one lane in flight (4: 431 us, 2: 397 us at ADP-64)
+    extern __shared__ float4 seg_sm[];                       // [RL][thread columns of the block]
+    const int tpr = C >> 2;
+    const int cpb = blockDim.x / RL;                         // thread columns per block = tpr * (nodes per block)
+    const int tc = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+    const int node = blockIdx.x * (cpb / tpr) + tc / tpr;
+    const int col = (tc % tpr) * 4;
+    const bool live = node < num_nodes;
+    const T* xc = x + col;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t* ptr = pass ? col_ptr : row_ptr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const int k1 = ptr[node + 1];
+            int k = ptr[node] + rl;
+            for (; k + (U - 1) * RL < k1; k += U * RL) {
+                int32_t r[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) r[u] = pass ? __ldg(perm + k + u * RL) : k + u * RL;
+                typename Raw4<T>::type v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = ld_raw4<T>(xc + (int64_t)r[u] * ldx);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float4 f = cvt_raw4(v[u]);
+                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                }
+            }
+            for (; k < k1; k += RL) {
+                const int32_t r0 = pass ? __ldg(perm + k) : k;
+                const float4 f = cvt_raw4(ld_raw4<T>(xc + (int64_t)r0 * ldx));
+                acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+            }
+        }
+        if (pass) __syncthreads();                           // lane 0 has finished reading the first pass's partial sums
+        seg_sm[rl * cpb + tc] = acc;
+        __syncthreads();
+        if (rl == 0 && live) {
+            for (int q = 1; q < RL; ++q) {
+                const float4 v = seg_sm[q * cpb + tc];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            store4<TO>(out + (int64_t)node * ldo + pass * C + col, acc);
+        }
+    }
+}
+
 template <typename T>
 __global__ void dsilu_mul_kernel(const float* __restrict__ dy, int64_t ld_dy, const typename ZOf<T>::type* __restrict__ z, int64_t ldz,
                                  T* __restrict__ y, int64_t ldy, int64_t rows, int C) {
@@ -1002,6 +1063,21 @@ int cartnet_segment_sum_pair(const void* x, int64_t ldx, const int32_t* row_ptr,
     if (num_nodes <= 0) return 0;
     const int npb = 256 / (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
+    static const int lanes_on = getenv("CARTNET_SEGSUM_LANES") ? atoi(getenv("CARTNET_SEGSUM_LANES")) : 1;      // 0: one thread column per node (A/B)
+    if (lanes_on) {
+        const int tpr = C / 4;
+        const int RL = tpr * 8 <= 1024 ? 8 : 1024 / tpr;                 // row lanes per node
+        const int nodes_pb = 1024 / (tpr * RL);                          // 1024-thread blocks
+        const size_t smem = 1024 * sizeof(float4);
+        CN_DISPATCH_PREC(prec, {
+            if (out_is_t)
+                segment_sum_pair_lanes_kernel<T, T><<<ceil_div(num_nodes, nodes_pb), 1024, smem, st>>>((const T*)x, ldx, row_ptr, col_ptr, perm_src, num_nodes, C, RL, (T*)out, ldo);
+            else
+                segment_sum_pair_lanes_kernel<T, float><<<ceil_div(num_nodes, nodes_pb), 1024, smem, st>>>((const T*)x, ldx, row_ptr, col_ptr, perm_src, num_nodes, C, RL, (float*)out, ldo);
+        });
+        CN_LAUNCH_CHECK();
+        return 0;
+    }
     CN_DISPATCH_PREC(prec, {
         if (out_is_t)
             segment_sum_pair_kernel<T, T><<<ceil_div(num_nodes, npb), 256, 0, st>>>((const T*)x, ldx, row_ptr, col_ptr, perm_src, num_nodes, C, (T*)out, ldo);
