@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcartnet_b200.so")
 
 PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3 = 0, 1, 2, 3
+NT_PAIR_MIN_ROWS = 32768      # include/cartnet_b200.h: CARTNET_NT_PAIR_MIN_ROWS
 ACT_NONE, ACT_SILU, ACT_MUL_DSILU = 0, 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float

@@ -92,6 +92,76 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
             : "memory");
     }
 }
+// ---- CTA pairs (cta_group::2). Two CTAs of a 2-CTA cluster (the two SMs of a TPC) run ONE M = 256 MMA: each CTA stages
+// its own 128 rows of A and HALF of the weight slice (BN/2 rows of B) in its own shared memory, the even ("leader") CTA's
+// single MMA thread issues tcgen05.mma.cta_group::2 which reads both CTAs' shared memory and writes rows 0..127 of the
+// accumulator into the leader's TMEM and rows 128..255 into the peer's. With the same 128 KB of weights per SM the pair
+// covers twice the output columns, so A crosses the L2 -> SM fabric half as often -- the fabric (~7.5 TB/s measured on
+// these GEMMs), not HBM, is what the 1-CTA kernel saturates when N / BN > 1. Protocol (as cute's SM100 2-SM atoms):
+// TMA loads of both CTAs signal the LEADER's full barrier (address with the peer bit cleared), the leader's commits are
+// multicast to both CTAs' empty / tmem_full barriers, both CTAs' epilogue warps arrive on the leader's tmem_empty.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;        // cute::Sm100MmaPeerBitMask: same offset in the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* slot, uint32_t ncols) {
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        tmem_alloc(slot, ncols);
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else tmem_dealloc(taddr, ncols);
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint64_t* bar) {
+    if (CG == 2) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    } else {
+        tc_commit(bar);
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    if (CG == 2) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                smem_u32(smem_dst)),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar) & kPeerBitMask)
+            : "memory");
+    } else {
+        tma_load_2d(smem_dst, map, c0, c1, bar);
+    }
+}
+// arrive on the pair leader's copy of a barrier (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_mma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        tc_mma<false>(tmem_d, adesc, bdesc, idesc, accumulate);
+    }
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = output row)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
@@ -347,7 +417,9 @@ struct NtBars {
 };
 constexpr int NT_STAT_BYTES = NT_EPI_WARPS * 2 * 128 * 4;          // per-warp [sum | sumsq][<= 128 columns] (EB_STATS only)
 
-template <typename T, int EPI>
+// CG = 1: one CTA per tile of 128 rows. CG = 2: a CTA pair per tile of 256 rows (see "CTA pairs" above; bf16 pairs only);
+// m_tiles counts tiles of 128 * CG rows, BN is the pair's column count (each CTA keeps BN / CG rows of B).
+template <typename T, int EPI, int CG = 1>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
              int BN, int n_tiles, int m_tiles, int stages, EpiParams<T> epi, double* __restrict__ stats) {
@@ -360,7 +432,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int kblks = K / TR::KB;
-    const int b_part_bytes = BN * 128;
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;       // 0 = the CTA (of a pair) that issues the MMAs
+    const int b_part_bytes = (BN / CG) * 128;
     const int b_kb_bytes = NP * b_part_bytes;
     uint8_t* smemB = smem;
     uint8_t* smemA = smem + (size_t)kblks * b_kb_bytes;
@@ -368,8 +441,9 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     NtBars* bars = reinterpret_cast<NtBars*>(reinterpret_cast<uint8_t*>(smemStg) + NT_STG_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x % n_tiles;
-    const int m_first = blockIdx.x / n_tiles, m_stride = gridDim.x / n_tiles;
+    const int unit = (int)blockIdx.x / CG, units = (int)gridDim.x / CG;      // CTA (pair) index
+    const int n_tile = unit % n_tiles;
+    const int m_first = unit / n_tiles, m_stride = units / n_tiles;
     const int n0 = n_tile * BN;
     const uint32_t tmem_cols = (uint32_t)(2 * BN < 32 ? 32 : 2 * BN);
 
@@ -378,23 +452,24 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_init(&bars->b_full, 1);
         // BN <= 32: only the first column group (4 warps) has columns; idle warps must not arrive (they would run ahead
         // of the MMA warp and complete phases it has not waited for yet)
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], BN > 32 ? NT_EPI_WARPS : NT_EPI_WARPS / 2); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], CG * (BN > 32 ? NT_EPI_WARPS : NT_EPI_WARPS / 2)); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&bars->tmem_slot, tmem_cols);
+    if (warp == 2) tmem_alloc_cg<CG>(&bars->tmem_slot, tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_slot;
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_expect_tx(&bars->b_full, (uint32_t)(kblks * b_kb_bytes));
+            if (rank == 0) mbar_expect_tx(&bars->b_full, (uint32_t)(CG * kblks * b_kb_bytes));      // both CTAs' halves
             for (int kb = 0; kb < kblks; ++kb)
 #pragma unroll
                 for (int pt = 0; pt < NP; ++pt)
-                    tma_load_2d(smemB + (size_t)kb * b_kb_bytes + pt * b_part_bytes, &tmB, (kb * NP + pt) * KBOX, n0, &bars->b_full);
+                    tma_load_2d_cg<CG>(smemB + (size_t)kb * b_kb_bytes + pt * b_part_bytes, &tmB, (kb * NP + pt) * KBOX, n0 + rank * (BN / CG), &bars->b_full);
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_stride) {
@@ -402,20 +477,29 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     // L2 prefetch of the same K block of this CTA's NEXT tile (one of the CTAs that share the tile does it)
                     if (prefetch && n_tile == 0 && mt + m_stride < m_tiles) {
 #pragma unroll
-                        for (int pt = 0; pt < NP; ++pt) tma_prefetch_2d(&tmA, (kb * NP + pt) * KBOX, (mt + m_stride) * 128);
+                        for (int pt = 0; pt < NP; ++pt) tma_prefetch_2d(&tmA, (kb * NP + pt) * KBOX, ((mt + m_stride) * CG + rank) * 128);
                     }
                     mbar_wait(&bars->a_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bars->a_full[stage], A_STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(&bars->a_full[stage], CG * A_STAGE_BYTES);
 #pragma unroll
                     for (int pt = 0; pt < NP; ++pt)
-                        tma_load_2d(smemA + stage * A_STAGE_BYTES + pt * NT_A_PART_BYTES, &tmA, (kb * NP + pt) * KBOX, mt * 128, &bars->a_full[stage]);
+                        tma_load_2d_cg<CG>(smemA + stage * A_STAGE_BYTES + pt * NT_A_PART_BYTES, &tmA, (kb * NP + pt) * KBOX, (mt * CG + rank) * 128, &bars->a_full[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (CG == 2) {
+                // the leader's last commits still arrive on this CTA's barriers: do not leave before every stage was released
+                for (int i = 0; i < stages; ++i) {
+                    mbar_wait(&bars->a_empty[stage], phase ^ 1);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        const uint32_t idesc = instr_desc(TR::FMT, 0, 0, 128, BN);
+        // ------------------------------------------------ MMA issuer (pairs: the leader CTA's only)
+        static_assert(CG == 1 || TR::NP == 2, "CTA pairs are built for the bf16-pair operands only");
+        if (rank == 0) {
+        const uint32_t idesc = instr_desc(TR::FMT, 0, 0, 128 * CG, BN);
         mbar_wait(&bars->b_full, 0);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
@@ -435,21 +519,22 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if (NP == 2) {      // split precision: the two cross terms first, then hi*hi, all into one fp32 accumulator
                             const uint64_t al = smem_desc(a_addr + NT_A_PART_BYTES + j * 32, 16, 1024);
                             const uint64_t bl = smem_desc(b_addr + b_part_bytes + j * 32, 16, 1024);
-                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), al, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), ad, bl, idesc, 1u);
-                            tc_mma<false>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, 1u);
+                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), al, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), ad, bl, idesc, 1u);
+                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, 1u);
                         } else {
                             tc_mma<TR::TF32>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
-                    tc_commit(&bars->a_empty[stage]);                  // frees the A stage when the MMAs retire
-                    if (kb == kblks - 1) tc_commit(&bars->tmem_full[acc]);
+                    tc_commit_cg<CG>(&bars->a_empty[stage]);           // frees the A stage (in both CTAs of a pair) when the MMAs retire
+                    if (kb == kblks - 1) tc_commit_cg<CG>(&bars->tmem_full[acc]);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
         }
     } else {
         // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> fused epilogue -> HBM
@@ -485,9 +570,10 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // 32-column blocks per warp), so each thread keeps the running sums of its 8 columns in registers over ALL its
         // tiles; the 8 row groups are combined once, at the end, by the same fixed butterfly
         constexpr bool kStatsRegs = kStats && TR::NP == 2;
-        float4 rs_s[2][NV], rs_q[2][NV];
+        constexpr int NBW = 2 * CG;                 // 32-column blocks per warp and tile (BN <= 128 * CG)
+        float4 rs_s[NBW][NV], rs_q[NBW][NV];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < NBW; ++a)
 #pragma unroll
             for (int h = 0; h < NV; ++h) rs_s[a][h] = rs_q[a][h] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kStats && !kStatsRegs) {
@@ -497,7 +583,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int mt = m_first; mt < m_tiles && c_begin < c_end; mt += m_stride) {
-            const int64_t row0 = (int64_t)mt * 128 + q * 32;
+            const int64_t row0 = ((int64_t)mt * CG + rank) * 128 + q * 32;
             // gather-row indices of the warp's 32 output rows, one row per lane (hoisted out of the column loop); the thread
             // that finishes row it * RPI + sub_r fetches its index with a shuffle
             int32_t i0v = 0, i1v = 0;
@@ -600,9 +686,9 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                 }
                 if (kStatsRegs) {
-                    const int cb = (c - c_begin) >> 5;          // 0 or 1
+                    const int cb = (c - c_begin) >> 5;          // 0 .. NBW-1
 #pragma unroll
-                    for (int a = 0; a < 2; ++a)
+                    for (int a = 0; a < NBW; ++a)
                         if (a == cb) {
 #pragma unroll
                             for (int h = 0; h < NV; ++h) {
@@ -616,14 +702,17 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&bars->tmem_empty[acc]);
+                else mbar_arrive(&bars->tmem_empty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
         if (kStatsRegs) {
-            const int64_t blk = (int64_t)(blockIdx.x / n_tiles) * 4 + q;
+            const int64_t blk = (int64_t)((unit / n_tiles) * CG + rank) * 4 + q;
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
+            for (int a = 0; a < NBW; ++a) {
                 if (c_begin + 32 * a >= c_end) break;
 #pragma unroll
                 for (int h = 0; h < NV; ++h) {
@@ -646,7 +735,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else if (kStats) {
             // one partial row per (m-CTA, TMEM lane quarter): [blk][sum | sumsq][N] fp64, summed in a fixed order afterwards
             __syncwarp();
-            const int64_t blk = (int64_t)(blockIdx.x / n_tiles) * 4 + q;
+            const int64_t blk = (int64_t)((unit / n_tiles) * CG + rank) * 4 + q;
             for (int i = lane; i < c_end - c_begin; i += 32) {
                 stats[(blk * 2 + 0) * N + n0 + c_begin + i] = (double)wstat[i];
                 stats[(blk * 2 + 1) * N + n0 + c_begin + i] = (double)wstat[128 + i];
@@ -654,8 +743,9 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) cluster_sync_all();      // the leader's MMAs read the peer's shared memory until its last commit
+    else __syncthreads();
+    if (warp == 2) tmem_dealloc_cg<CG>(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ TN kernel
@@ -833,8 +923,26 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const v
     return 0;
 }
 
+// launches a CG = 2 instantiation as clusters of two CTAs
+template <typename K, typename E>
+static int launch_pair(K kernel, int grid, size_t smem, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int Kd,
+                       int BN, int n_tiles, int m_tiles, int stages, const E& epi, double* stats) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CN_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, Kd, BN, n_tiles, m_tiles, stages, epi, stats));
+    return 0;
+}
+
 template <typename T>
-static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks) {
+static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* stats_blocks, bool allow_pair = true) {
     using TR = TcTraits<T>;
     constexpr int NP = TR::NP;
     const int slot = (int)sizeof(T);          // shared-memory bytes per operand element (pairs: hi + lo)
@@ -858,18 +966,34 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
         if (BN) break;
     }
     CN_CHECK_ARG(BN > 0, "tcgen05 gemm: no resident tile for N=%d K=%d", d.N, d.K);
-    const int n_tiles = d.N / BN, m_tiles = ceil_div(d.M, 128);
-    CN_CHECK_ARG(n_tiles <= kNumSMs, "tcgen05 gemm: too many N tiles (%d)", n_tiles);
-    int grid = (kNumSMs / n_tiles) * n_tiles;
-    if ((int64_t)grid > (int64_t)m_tiles * n_tiles) grid = m_tiles * n_tiles;
+    // CTA pairs (cta_group::2): each CTA keeps half of the pair's weight slice, so the pair covers twice the columns with
+    // the same shared memory and A crosses the L2 -> SM fabric half as often. Edge-sized GEMMs of the pair mode only.
+    const char* cg_str = getenv("CARTNET_NT_CG");                 // "1": never pair (A/B runs and the pair-vs-single tests; read per call)
+    const int cg_env = cg_str ? atoi(cg_str) : 2;
+    int CG = 1;
+    if (NP == 2 && cg_env == 2 && allow_pair && d.M >= CARTNET_NT_PAIR_MIN_ROWS && BN < d.N) {
+        for (int cand : {256, 128, 64}) {
+            if (cand <= BN || cand > 2 * bn_cap || (int64_t)(cand / 2) * d.K * slot > 131072 || d.N % cand != 0) continue;
+            for (int ns : {NT_STAGES, 2}) {
+                const size_t need = 1024 + (size_t)(cand / 2) * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64;
+                if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; CG = 2; break; }
+            }
+            if (CG == 2) break;
+        }
+    }
+    const int n_tiles = d.N / BN, m_tiles = ceil_div(d.M, 128 * CG);
+    CN_CHECK_ARG(n_tiles <= kNumSMs / CG, "tcgen05 gemm: too many N tiles (%d)", n_tiles);
+    int units = (kNumSMs / CG / n_tiles) * n_tiles;                // CTAs, or CTA pairs
+    if ((int64_t)units > (int64_t)m_tiles * n_tiles) units = m_tiles * n_tiles;
+    const int grid = units * CG;
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, TR::DT, TR::TMA_ES, d.A, d.M, (int64_t)NP * d.K, NP * d.lda, 128 / TR::TMA_ES, 128);
     if (rc) return rc;
-    rc = make_map(&tmB, TR::DT, TR::TMA_ES, d.B, d.N, (int64_t)NP * d.K, NP * d.ldb, 128 / TR::TMA_ES, BN);
+    rc = make_map(&tmB, TR::DT, TR::TMA_ES, d.B, d.N, (int64_t)NP * d.K, NP * d.ldb, 128 / TR::TMA_ES, BN / CG);
     if (rc) return rc;
-    if (stats_blocks) *stats_blocks = (grid / n_tiles) * 4;
+    if (stats_blocks) *stats_blocks = (units / n_tiles) * CG * 4;
     static const int pf_env = getenv("CARTNET_NT_PREFETCH") ? atoi(getenv("CARTNET_NT_PREFETCH")) : 1;     // tuning knob (experiments)
-    if (pf_env && m_tiles > grid / n_tiles) stages |= 16;
+    if (pf_env && m_tiles > units / n_tiles) stages |= 16;
     int mask = 0;
     if (stats) mask |= EB_STATS;
     if (d.bias) mask |= EB_BIAS;
@@ -884,6 +1008,13 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     const EpiParams<T> epi = make_epi<T>(d);
 #define CN_NT_CASE(M_)                                                                                               \
     if (mask == (M_)) {                                                                                              \
+        if constexpr (NP == 2) {                                                                                     \
+            if (CG == 2) {                                                                                           \
+                static bool attr2_done[64] = {};                                                                     \
+                if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_), 2>, attr2_done)) return rc_;                     \
+                return launch_pair(tc_nt_kernel<T, (M_), 2>, grid, smem, st, tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, stages, epi, stats); \
+            }                                                                                                        \
+        }                                                                                                            \
         static bool attr_done[64] = {};                                                                              \
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_)>, attr_done)) return rc_;                                 \
         tc_nt_kernel<T, (M_)><<<grid, NT_THREADS, smem, st>>>(tmA, tmB, d.M, d.N, d.K, BN, n_tiles, m_tiles, stages, epi, stats); \
@@ -907,6 +1038,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     CN_NT_CASE(EB_BIAS | EB_ZOUT | EB_SILU | EB_OUTF)                     // edge encoder, second Linear (tf32)
 #undef CN_NT_CASE
     CN_CHECK_ARG(!stats, "tcgen05 gemm: fused column statistics need the bias + T-output epilogue");
+    if (CG == 2) return run_nt<T>(d, st, stats, stats_blocks, false);      // CTA pairs exist for the specialised epilogues only
     {
         static bool attr_done[64] = {};
         if (int rc_ = ensure_big_smem(tc_nt_kernel<T, EPI_GENERIC>, attr_done)) return rc_;

@@ -188,11 +188,12 @@ int cartnet_layer_bwd(const cartnet_layer_t* L, cartnet_stream_t st) {
     CN_TRY(cartnet_gemm_tn(prec, D, D, E, L->dg_t, D, L->H, 2 * D, L->dG2, D, L->splitk, L->splitk_bytes, st));
     CN_TRY(cartnet_gemm_tn(prec, D, D, E, L->ds_t, D, toff((const void*)L->H, prec, D), 2 * D, L->dA2, D, L->splitk, L->splitk_bytes, st));
     // first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
-    if (prec == CARTNET_PREC_BF16X3) {
-        // pair operands: the resident weight slice for K = 2D would be only 64 rows (128 KB / (2D x 4 B)), i.e. four passes
-        // over dZ per launch with two 32 KB stages in flight (measured 0.80 ms, 53 % of HBM). The two K halves -- the gate
-        // and the aggregate branch -- are contracted by two launches with 128-row slices instead, the second accumulating
-        // onto the first through the residual input (same element, same thread): 2 x 0.31 ms.
+    if (prec == CARTNET_PREC_BF16X3 && E < CARTNET_NT_PAIR_MIN_ROWS) {
+        // pair operands on a single CTA per tile: the resident weight slice for K = 2D would be only 64 rows (128 KB /
+        // (2D x 4 B)), i.e. four passes over dZ per launch with two 32 KB stages in flight (measured 0.80 ms at ADP-64). The
+        // two K halves -- the gate and the aggregate branch -- are contracted by two launches with 128-row slices instead,
+        // the second accumulating onto the first through the residual input (same element, same thread): 2 x 0.37 ms.
+        // Edge counts that run as CTA pairs (cta_group::2, 128 columns per pair at K = 2D) take ONE launch: 0.60 ms.
         for (int h = 0; h < 2; ++h) {
             cartnet_gemm_t d = gemm_desc(prec, (int)E, D, D, toff((const void*)L->dZ, prec, (int64_t)h * D), 2 * D,
                                          toff((const void*)L->W1eT_t, prec, (int64_t)h * D), 2 * D);

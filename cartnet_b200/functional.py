@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import NT_PAIR_MIN_ROWS
 from .ops import ACT_MUL_DSILU, ACT_SILU, PREC_BF16, PREC_BF16X3, PREC_FP32, PREC_TF32, f32_storage, needs_shadow, t_dtype, z_dtype
 
 
@@ -272,7 +273,7 @@ class _LayerFn(torch.autograd.Function):
         # first Linear, edge part: de = dZ W1e + de_out (residual e' = e + sig)
         de_in = torch.empty(E, D, dtype=torch.float32, device=dev)
         W1eT = _to_t(W1e.t(), prec)
-        if prec == PREC_BF16X3:      # as in csrc/layer.cu: the gate and aggregate K halves as two launches with 128-row weight slices
+        if prec == PREC_BF16X3 and E < NT_PAIR_MIN_ROWS:      # as in csrc/layer.cu: two K-half launches unless the GEMM runs as CTA pairs
             for h in range(2):
                 ops.gemm(prec, dZ[:, h * D:(h + 1) * D], W1eT[:, h * D:(h + 1) * D], resid=de_out if h == 0 else de_in, out_f32=de_in)
         else:

@@ -36,6 +36,9 @@ extern "C" {
 typedef void* cartnet_stream_t; /* cudaStream_t */
 
 enum { CARTNET_PREC_FP32 = 0, CARTNET_PREC_BF16 = 1, CARTNET_PREC_TF32 = 2, CARTNET_PREC_BF16X3 = 3 };
+/* BF16X3 GEMMs with at least this many rows run as CTA pairs (tcgen05 cta_group::2: one M = 256 MMA per two SMs, each SM
+ * keeping half of the pair's weight slice); the layer picks its launch shapes accordingly. Results do not depend on it. */
+#define CARTNET_NT_PAIR_MIN_ROWS 32768
 enum { CARTNET_ACT_NONE = 0, CARTNET_ACT_SILU = 1, CARTNET_ACT_MUL_DSILU = 2 };
 
 int cartnet_version(void);
