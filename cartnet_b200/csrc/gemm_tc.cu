@@ -425,7 +425,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              int BN, int n_tiles, int m_tiles, int stages, EpiParams<T> epi, double* __restrict__ stats) {
     using TR = TcTraits<T>;
     constexpr int NP = TR::NP;
-    const bool prefetch = (stages & 16) != 0;        // host flag folded into `stages`
+    const bool prefetch = (stages & 16) != 0;        // host flags folded into `stages`
+    const bool uni_path = (stages & 32) != 0;        // gather0 rows that are equal over a warp's 32 rows are loaded once
     stages &= 15;
     constexpr int KBOX = 128 / TR::TMA_ES;           // TMA elements per 128-byte box row
     constexpr int A_STAGE_BYTES = NP * NT_A_PART_BYTES;
@@ -593,6 +594,10 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 i1v = (row < M && epi.gather1 != nullptr) ? epi.gidx1[row] : 0;
             }
             const bool full = row0 + 32 <= (int64_t)M;
+            // gather0 is indexed by the CSR-sorted destination: ~70 % of the 32-row blocks have ONE destination, whose row is
+            // then loaded once per thread instead of once per row (-3 KB of the 22 KB a block moves through the LSU)
+            const bool uni = uni_path && epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr) &&
+                             __all_sync(0xffffffffu, i0v == __shfl_sync(0xffffffffu, i0v, 0));
             bool first = true;
             for (int c = c_begin; c < c_end; c += 32) {
                 const int col = n0 + c + sub_c;
@@ -622,7 +627,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const int32_t i0 = has_g0 ? __shfl_sync(0xffffffffu, i0v, it * RPI + sub_r) : 0;
                     const int32_t i1 = has_g1 ? __shfl_sync(0xffffffffu, i1v, it * RPI + sub_r) : 0;
                     if (full || row < M) {
-                        if (has_g0) ldv(ra[it], epi.gather0 + (int64_t)i0 * epi.ldg + col);
+                        if (has_g0 && (!uni || it == 0)) ldv(ra[it], epi.gather0 + (int64_t)i0 * epi.ldg + col);
                         if (has_g1) ldv(rb[it], epi.gather1 + (int64_t)i1 * epi.ldg + col);
                         if (has_z) ldv(rz[it], epi.z_in + row * epi.ldzin + col);
                         if (has_r) {
@@ -661,7 +666,10 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         float4 ga[NV], gb[NV], zi[NV], zv[NV], o[NV];
 #pragma unroll
                         for (int h = 0; h < NV; ++h) ga[h] = gb[h] = zi[h] = zero;
-                        if (has_g0) cvtv(ra[it], ga);
+                        if (has_g0) {
+                            if (uni) cvtv(ra[0], ga);
+                            else cvtv(ra[it], ga);
+                        }
                         if (has_g1) cvtv(rb[it], gb);
                         if (has_z) cvtv(rz[it], zi);
 #pragma unroll
@@ -994,6 +1002,8 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     if (stats_blocks) *stats_blocks = (units / n_tiles) * CG * 4;
     static const int pf_env = getenv("CARTNET_NT_PREFETCH") ? atoi(getenv("CARTNET_NT_PREFETCH")) : 1;     // tuning knob (experiments)
     if (pf_env && m_tiles > units / n_tiles) stages |= 16;
+    const char* uni_str = getenv("CARTNET_NT_UNIFORM");             // "0": always one gather0 load per row (A/B)
+    if (!uni_str || atoi(uni_str) != 0) stages |= 32;
     int mask = 0;
     if (stats) mask |= EB_STATS;
     if (d.bias) mask |= EB_BIAS;

@@ -94,7 +94,7 @@ def test_gemm_fused_epilogues():
     assert common.rel_err(o, o_r) < 3e-5
 
 
-@pytest.mark.parametrize("N,K", [(256, 256), (512, 256), (256, 512), (512, 128)])
+@pytest.mark.parametrize("N,K", [(256, 256), (512, 256), (256, 512), (512, 128), (512, 512), (1024, 512), (512, 1024), (128, 256), (192, 64)])
 def test_cta_pair_gemms_equal_single_cta_gemms(N, K, monkeypatch):
     """Edge-sized GEMMs (M >= 32768) run as CTA pairs (tcgen05 cta_group::2: M = 256 per MMA, half of the weight slice per
     SM). Same products in the same order per output element -> bit-identical to the single-CTA kernel, for every fused
