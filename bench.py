@@ -434,6 +434,11 @@ def run_ours(args, wl):
     ms_step = ms / args.steps
     value = world * graphs_step / (ms_step * 1e-3)
 
+    if os.environ.get("CARTNET_BENCH_PROFILE_ONLY") == "1":      # ncu launch lists (scripts/step_traffic.py): the timed loop is all that is wanted
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_step, "note": "not a bench line"}))
+        return
+
     # ---- end to end through the public API: pinned host batch -> .to(device) -> model -> result read back on the host
     h2d = int(np.mean([batch_bytes(b) for b in host_batches]))
 
