@@ -1001,7 +1001,9 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     if (rc) return rc;
     if (stats_blocks) *stats_blocks = (units / n_tiles) * CG * 4;
     static const int pf_env = getenv("CARTNET_NT_PREFETCH") ? atoi(getenv("CARTNET_NT_PREFETCH")) : 1;     // tuning knob (experiments)
-    if (pf_env && m_tiles > units / n_tiles) stages |= 16;
+    // CTA pairs read every A tile once, from one SM: the prefetch only adds DRAM reads there (ncu: +0.1..0.3 GB per launch,
+    // step 28.1 -> 27.8 ms without it) except for the two-stage K >= 512 ring, which still gains 2 %
+    if (pf_env && m_tiles > units / n_tiles && (CG == 1 || d.K >= 512)) stages |= 16;
     const char* uni_str = getenv("CARTNET_NT_UNIFORM");             // "0": always one gather0 load per row (A/B)
     if (!uni_str || atoi(uni_str) != 0) stages |= 32;
     int mask = 0;
