@@ -149,16 +149,22 @@ __device__ __forceinline__ void tma_load_2d_cg(void* smem_dst, const CUtensorMap
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
-template <int CG>
-__device__ __forceinline__ void tc_mma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (CG == 2) {
+template <bool TF32, int CG>
+__device__ __forceinline__ void tc_mma_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 2 && TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (CG == 2) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     } else {
-        tc_mma<false>(tmem_d, adesc, bdesc, idesc, accumulate);
+        tc_mma<TF32>(tmem_d, adesc, bdesc, idesc, accumulate);
     }
 }
 
@@ -417,7 +423,7 @@ struct NtBars {
 };
 constexpr int NT_STAT_BYTES = NT_EPI_WARPS * 2 * 128 * 4;          // per-warp [sum | sumsq][<= 128 columns] (EB_STATS only)
 
-// CG = 1: one CTA per tile of 128 rows. CG = 2: a CTA pair per tile of 256 rows (see "CTA pairs" above; bf16 pairs only);
+// CG = 1: one CTA per tile of 128 rows. CG = 2: a CTA pair per tile of 256 rows (see "CTA pairs" above; 4-byte operands);
 // m_tiles counts tiles of 128 * CG rows, BN is the pair's column count (each CTA keeps BN / CG rows of B).
 template <typename T, int EPI, int CG = 1>
 __global__ void __launch_bounds__(NT_THREADS, 1)
@@ -498,7 +504,7 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (pairs: the leader CTA's only)
-        static_assert(CG == 1 || TR::NP == 2, "CTA pairs are built for the bf16-pair operands only");
+        static_assert(CG == 1 || sizeof(T) == 4, "CTA pairs are built for the 4-byte operand modes (bf16 pairs, tf32)");
         if (rank == 0) {
         const uint32_t idesc = instr_desc(TR::FMT, 0, 0, 128 * CG, BN);
         mbar_wait(&bars->b_full, 0);
@@ -520,11 +526,11 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if (NP == 2) {      // split precision: the two cross terms first, then hi*hi, all into one fp32 accumulator
                             const uint64_t al = smem_desc(a_addr + NT_A_PART_BYTES + j * 32, 16, 1024);
                             const uint64_t bl = smem_desc(b_addr + b_part_bytes + j * 32, 16, 1024);
-                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), al, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), ad, bl, idesc, 1u);
-                            tc_mma_f16_cg<CG>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, 1u);
+                            tc_mma_cg<false, CG>(tmem_base + (uint32_t)(acc * BN), al, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            tc_mma_cg<false, CG>(tmem_base + (uint32_t)(acc * BN), ad, bl, idesc, 1u);
+                            tc_mma_cg<false, CG>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, 1u);
                         } else {
-                            tc_mma<TR::TF32>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            tc_mma_cg<TR::TF32, CG>(tmem_base + (uint32_t)(acc * BN), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     tc_commit_cg<CG>(&bars->a_empty[stage]);           // frees the A stage (in both CTAs of a pair) when the MMAs retire
@@ -975,15 +981,16 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     }
     CN_CHECK_ARG(BN > 0, "tcgen05 gemm: no resident tile for N=%d K=%d", d.N, d.K);
     // CTA pairs (cta_group::2): each CTA keeps half of the pair's weight slice, so the pair covers twice the columns with
-    // the same shared memory and A crosses the L2 -> SM fabric half as often. Edge-sized GEMMs of the pair mode only.
+    // the same shared memory and A crosses the L2 -> SM fabric half as often. Edge-sized GEMMs of the 4-byte operand modes.
     const char* cg_str = getenv("CARTNET_NT_CG");                 // "1": never pair (A/B runs and the pair-vs-single tests; read per call)
     const int cg_env = cg_str ? atoi(cg_str) : 2;
     int CG = 1;
-    if (NP == 2 && cg_env == 2 && allow_pair && d.M >= CARTNET_NT_PAIR_MIN_ROWS && BN < d.N) {
+    if (slot == 4 && cg_env == 2 && allow_pair && d.M >= CARTNET_NT_PAIR_MIN_ROWS && BN < d.N) {
         for (int cand : {256, 128, 64}) {
             if (cand <= BN || cand > 2 * bn_cap || (int64_t)(cand / 2) * d.K * slot > 131072 || d.N % cand != 0) continue;
             for (int ns : {NT_STAGES, 2}) {
-                const size_t need = 1024 + (size_t)(cand / 2) * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64;
+                const size_t need = 1024 + (size_t)(cand / 2) * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
+                                    ((stats && !stats_in_regs) ? NT_STAT_BYTES : 0);
                 if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; CG = 2; break; }
             }
             if (CG == 2) break;
@@ -1020,7 +1027,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     const EpiParams<T> epi = make_epi<T>(d);
 #define CN_NT_CASE(M_)                                                                                               \
     if (mask == (M_)) {                                                                                              \
-        if constexpr (NP == 2) {                                                                                     \
+        if constexpr (sizeof(T) == 4) {                                                                              \
             if (CG == 2) {                                                                                           \
                 static bool attr2_done[64] = {};                                                                     \
                 if (int rc_ = ensure_big_smem(tc_nt_kernel<T, (M_), 2>, attr2_done)) return rc_;                     \
