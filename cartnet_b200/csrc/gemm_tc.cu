@@ -410,7 +410,7 @@ __device__ __forceinline__ void stats_flushv(float* wstat, int cidx, int lane, f
 }
 
 // ------------------------------------------------------------------------------------------ NT kernel
-constexpr int NT_STAGES = 3;                     // at most; the host picks 2 when the operands are pairs and the weight slice is large
+constexpr int NT_STAGES = 6;                     // at most; the host picks the deepest ring that fits next to the weight slice
 constexpr int NT_A_PART_BYTES = 128 * 128;       // 128 rows x 128 B (one operand part of one K block)
 constexpr int NT_EPI_WARPS = 8;
 constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
@@ -972,7 +972,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     const bool stats_in_regs = stats && NP == 2;            // pairs: per-thread running sums, at most two column blocks per warp
     for (int cand : {256, 128, 64, 32}) {
         if (cand > bn_cap || (int64_t)cand * d.K * slot > 131072 || d.N % cand != 0 || (stats_in_regs && cand > 128)) continue;
-        for (int ns : {NT_STAGES, 2}) {
+        for (int ns : {6, 5, 4, 3, 2}) {
             const size_t need = 1024 + (size_t)cand * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
                                 ((stats && !stats_in_regs) ? NT_STAT_BYTES : 0);
             if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; break; }
@@ -988,7 +988,7 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     if (slot == 4 && cg_env == 2 && allow_pair && d.M >= CARTNET_NT_PAIR_MIN_ROWS && BN < d.N) {
         for (int cand : {256, 128, 64}) {
             if (cand <= BN || cand > 2 * bn_cap || (int64_t)(cand / 2) * d.K * slot > 131072 || d.N % cand != 0) continue;
-            for (int ns : {NT_STAGES, 2}) {
+            for (int ns : {6, 5, 4, 3, 2}) {
                 const size_t need = 1024 + (size_t)(cand / 2) * d.K * slot + (size_t)ns * NP * NT_A_PART_BYTES + NT_STG_BYTES + sizeof(NtBars) + 64 +
                                     ((stats && !stats_in_regs) ? NT_STAT_BYTES : 0);
                 if (need <= (size_t)227 * 1024) { BN = cand; stages = ns; smem = need; CG = 2; break; }
