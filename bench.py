@@ -198,9 +198,11 @@ def cpu_reference_batch(wl, batch: int, seed: int, sample: int, atoms):
     return fixtures.make_oracle_batch(wl["shape"], sample, seed, sizes=sizes, cholesky=wl["model"]["cholesky"], temperature=True)
 
 
-def cpu_reference_step_time(wl, hb, steps: int, warmup: int):
+def cpu_reference_step_time(wl, hb, steps: int, warmup: int, budget_s: float = None):
     """The reference algorithm (oracle port of models/cartnet.py, eager PyTorch fp32 on CPU, all host threads):
-    train = fwd + L1 + bwd + Adam, eval = forward under no_grad. Returns (s/step, graphs, edges)."""
+    train = fwd + L1 + bwd + Adam, eval = forward under no_grad. Returns (s/step, graphs, edges, timed steps).
+    budget_s bounds the wall time: the full ADP batch takes ~12 s per step on 16 cores, so W + K = 25 steps would run for
+    five minutes; once the budget is spent (and at least one warm-up and two timed steps are done) the loop stops."""
     from oracle import cartnet_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
@@ -209,7 +211,15 @@ def cpu_reference_step_time(wl, hb, steps: int, warmup: int):
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     model.train(train)
     times = []
-    for it in range(warmup + steps):
+    t_start = time.perf_counter()
+    it = -1
+    while len(times) < steps:
+        it += 1
+        spent = time.perf_counter() - t_start
+        if budget_s is not None and spent > budget_s and len(times) >= 2:
+            break
+        if budget_s is not None and spent > 0.4 * budget_s and it >= 1 and it < warmup:
+            warmup = it                      # out of warm-up budget: start timing
         t0 = time.perf_counter()
         if train:
             opt.zero_grad(set_to_none=True)
@@ -222,7 +232,7 @@ def cpu_reference_step_time(wl, hb, steps: int, warmup: int):
                 model(shallow(hb))
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), int(hb.natoms.numel()), int(hb.edge_index.shape[1])
+    return float(np.mean(times)), int(hb.natoms.numel()), int(hb.edge_index.shape[1]), len(times)
 
 
 def run_reference(args, wl):
@@ -232,7 +242,7 @@ def run_reference(args, wl):
     # none of the product's kernels on this arm: the graphs come from the oracle graph builder (CPU)
     sample, atoms = cpu_sample_plan(wl, args.batch, args.cpu_sample)
     hb = cpu_reference_batch(wl, args.batch, args.seed, sample, atoms)
-    sec, graphs, edges = cpu_reference_step_time(wl, hb, args.steps, args.warmup)
+    sec, graphs, edges, n_timed = cpu_reference_step_time(wl, hb, args.steps, args.warmup, budget_s=args.cpu_budget_s)
     cores = os.cpu_count() or 1
     val = graphs / sec
     full = graphs == args.batch and not atoms
@@ -244,7 +254,7 @@ def run_reference(args, wl):
         "config": {"workload": (wl["desc"] % args.batch) + " -- reference algorithm (oracle port of models/cartnet.py) on the host CPU",
                    "baseline_config": wl["config"], "name": args.workload, "crystals_per_step": graphs, "edges_per_step": edges, "full_batch": full},
         "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": cores, "kind": "port",
-                         "sample": "%s (%d edges) of the workload's batch per step" % (what, edges)},
+                         "sample": "%s (%d edges) of the workload's batch per step; %d timed steps (wall budget %d s)" % (what, edges, n_timed, int(args.cpu_budget_s))},
         "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
@@ -549,7 +559,7 @@ def run_ours(args, wl):
     if world == 1 and not args.no_cpu_baseline:
         sample, atoms = cpu_sample_plan(wl, args.batch, args.cpu_sample)
         hb = cpu_reference_batch(wl, args.batch, args.seed, sample, atoms)
-        sec, g, e = cpu_reference_step_time(wl, hb, 2, 1)
+        sec, g, e, _ = cpu_reference_step_time(wl, hb, 2, 1)
         cpu = {"value": g / sec, "unit": "graphs/s", "cores": os.cpu_count() or 1, "kind": "port", "edges_per_sec": e / sec,
                "sample": "%d crystals (%d edges)%s of the workload's batch, %s, 1 warm-up + mean of 2" % (
                    g, e, " = the full batch" if (g == args.batch and not atoms) else "", "fwd+bwd+Adam" if train else "eval forward")}
@@ -593,6 +603,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="crystals per GPU (default: the workload's)")
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None, help="crystals per step for the CPU reference (default: the full batch where the oracle finishes in seconds)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-time bound of the CPU loop (>= 1 warm-up + 2 timed steps always run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-precision", action="store_true")
     args = ap.parse_args()
