@@ -2,13 +2,17 @@
 // CARTNET_PREC_TF32: kind::tf32 on fp32 words that were rounded to tf32 where they were produced). Hand-written PTX; descriptor bit
 // layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 //
+// CARTNET_PREC_BF16X3: kind::f16 on hi|lo bf16 pairs, three MMAs per product (common.cuh::bf16p_t).
+//
 // NT kernel  C[M,N] = A[M,K] B[N,K]^T  (+ fused epilogue, gemm_epilogue.cuh)
-//   * persistent, one CTA per SM; the CTA's 128 KB weight slice B[n0:n0+BN, 0:K] is loaded ONCE by TMA and
+//   * persistent, one CTA per SM; the CTA's <= 128 KB weight slice B[n0:n0+BN, 0:K] is loaded ONCE by TMA and
 //     stays resident in shared memory (K-major, 128B swizzle), so per 128-row tile only A streams through a
-//     3-stage TMA/mbarrier ring (16 KB per stage) -- weights never re-cross L2->SM per tile;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread, tcgen05.mma cta_group::1, M=128, N=BN),
+//     2..6-stage TMA/mbarrier ring -- weights never re-cross L2->SM per tile;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread, tcgen05.mma, M=128, N=BN),
 //     warps 2..9 = epilogue: tcgen05.ld 32 columns at a time from one of TWO TMEM accumulators, so the
-//     epilogue of tile i overlaps the MMAs of tile i+1; gathers / bias / SiLU / stores are fused there.
+//     epilogue of tile i overlaps the MMAs of tile i+1; gathers / bias / SiLU / stores are fused there;
+//   * edge-sized GEMMs of the 4-byte operand modes run as CTA PAIRS (cta_group::2, M = 256): each SM keeps half of the
+//     pair's weight slice, so a pair covers twice the columns and A is streamed half as often (see "CTA pairs").
 //
 // TN kernel  C[M,N] = sum_k A[k,M]^T B[k,N]  (weight gradients; K = edges or nodes, split over CTAs)
 //   * both operands are MN-major as they lie in HBM ([k, mn] row-major), fed by TMA boxes of
