@@ -3,7 +3,8 @@ signatures, state-dict keys and `forward(batch)` contract, including the in-plac
 `batch.x` / `batch.edge_attr`), with the edge branch of the encoder and the whole `CartNet_layer`
 running on hand-written sm_100a kernels through the C ABI in include/cartnet_b200.h.
 
-What stays plain PyTorch (node-side, negligible cost): the atom embedding branch
+What stays plain PyTorch (node-side, negligible cost): the atom embedding lookup (with a deterministic
+backward of its own, functional._EmbeddingRowsFn) and the temperature branch
 of the encoder and the two heads.
 
 Reference quirks that are preserved on purpose:
@@ -223,6 +224,13 @@ class Encoder(nn.Module, _PrecisionMixin):
                                           nn.Linear(dim_in * 2, dim_in), self.activation)
         self.rbf = ExpNormalSmearingParams(radius, dim_rbf)
 
+    def _embed(self, idx):
+        """nn.Embedding lookup (cartnet.py:146,149); 1-D index tensors take the library's deterministic backward
+        (functional._EmbeddingRowsFn), anything else falls back to the module's own forward."""
+        if idx.dim() == 1 and idx.dtype == torch.int64 and int(self.embedding.weight.shape[1]) % 4 == 0:
+            return CF.embedding_rows(self.embedding.weight, idx)
+        return self.embedding(idx)
+
     def forward(self, batch):
         # Edge branch first (cartnet.py:156-159): its three launches are ~1 ms of device work, issued before the ~30 small
         # node-side launches below so that the GPU is busy while the host walks through those (the two branches are
@@ -246,9 +254,9 @@ class Encoder(nn.Module, _PrecisionMixin):
             batch.edge_attr = _tag(e0, e0_t, self.prec)
 
         if self.temperature and self.atom_types:                                   # cartnet.py:144-151
-            x = self.embedding(batch.x) + _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
+            x = self._embed(batch.x) + _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
         elif not self.temperature and self.atom_types:
-            x = self.embedding(batch.x) + self.bias
+            x = self._embed(batch.x) + self.bias
         elif self.temperature and not self.atom_types:
             x = _per_graph_rows(self.temperature_proj_atom(batch.temperature.unsqueeze(-1)), batch)
         else:

@@ -120,6 +120,55 @@ def linear_silu(x, W, b, prec):
     return _LinearSiluFn.apply(x, W, b, prec)
 
 
+class _EmbeddingRowsFn(torch.autograd.Function):
+    """y = W[idx] -- nn.Embedding's forward (/root/reference/models/cartnet.py:113,146) with a DETERMINISTIC backward.
+    torch's CUDA embedding backward accumulates partial segments with float atomics once there are more than 3072 indices
+    (the ADP-64 batch has 12.5 k atoms): the one gradient of a training step that was not bit-reproducible. Here the rows
+    of dy are grouped by index with a stable sort and summed in a fixed order in two levels -- pieces of at most 64
+    consecutive rows of one index (many short segments: parallel), then the pieces of each index -- both by the library's
+    CSR segment sum. No host synchronisation: the piece table has a fixed upper size and is padded with empty pieces."""
+
+    PIECE = 64
+
+    @staticmethod
+    def forward(ctx, W, idx):
+        ctx.save_for_backward(idx)
+        ctx.rows = int(W.shape[0])
+        return W.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        T, N, C = ctx.rows, int(idx.numel()), int(dy.shape[1])
+        dev = dy.device
+        out = torch.zeros(T, C, dtype=torch.float32, device=dev)
+        if N == 0:
+            return out, None
+        R = _EmbeddingRowsFn.PIECE
+        order = torch.sort(idx, stable=True)
+        sidx, perm = order.values, order.indices.to(torch.int32)
+        counts = torch.bincount(idx, minlength=T)
+        tstart = torch.cumsum(counts, 0) - counts                       # first sorted position of every index value
+        pos = torch.arange(N, device=dev) - tstart[sidx]                # position inside its group
+        first = (pos % R) == 0                                          # row opens a piece
+        piece = torch.cumsum(first.to(torch.int64), 0) - 1              # piece id of every sorted row
+        P = (N + R - 1) // R + T                                        # upper bound on the number of pieces
+        ptr1 = torch.full((P + 1,), N, dtype=torch.int32, device=dev)   # unused pieces are empty ([N, N))
+        rows = torch.arange(N, device=dev, dtype=torch.int32)
+        ptr1[piece[first]] = rows[first]
+        part = torch.empty(P, C, dtype=torch.float32, device=dev)
+        ops.segment_sum(dy.contiguous(), ptr1, perm, P, part, PREC_FP32)
+        # pieces of one index value are consecutive: its first piece is the piece of its first sorted row
+        piece_ext = torch.cat([piece, piece[-1:] + 1])
+        ptr2 = torch.cat([piece_ext[tstart.clamp(max=N)], piece_ext[-1:]]).to(torch.int32)
+        ops.segment_sum(part, ptr2, None, T, out, PREC_FP32)
+        return out, None
+
+
+def embedding_rows(W, idx):
+    return _EmbeddingRowsFn.apply(W, idx)
+
+
 class _CholeskyTailFn(torch.autograd.Function):
     """(h [n, Dh], W1 [6, Dh], b1 [6]) -> U [n,3,3] = L^T L with L upper triangular, softplus diagonal
     (/root/reference/models/cartnet.py:293-303): one launch forward, two backward."""

@@ -217,7 +217,8 @@ def edge_gate_bwd(gn_t, s_t, dist, dst32, de_out, dm, bn_var, bn_w, bn_b, radius
 def segment_sum(x, ptr, perm, num_nodes, out, prec):
     counts = (ptr[1:] - ptr[:-1]).long()
     seg = torch.repeat_interleave(torch.arange(num_nodes), counts)
-    rows = _f(x) if perm is None else _f(x)[perm.long()]
+    n = int(ptr[-1])                       # rows beyond the last segment are not read (the kernels walk the CSR rows only)
+    rows = _f(x)[:n] if perm is None else _f(x)[perm.long()[:n]]
     res = torch.zeros(num_nodes, x.shape[1], dtype=rows.dtype).index_add_(0, seg, rows)
     out_is_t = not (out.dtype == torch.float32 and not f32_storage(prec))
     out.copy_(_shadow(res, prec) if out_is_t else res.to(out.dtype))
