@@ -147,15 +147,16 @@ class _EmbeddingRowsFn(torch.autograd.Function):
         R = _EmbeddingRowsFn.PIECE
         order = torch.sort(idx, stable=True)
         sidx, perm = order.values, order.indices.to(torch.int32)
-        counts = torch.bincount(idx, minlength=T)
+        counts = torch.zeros(T, dtype=torch.int64, device=dev).scatter_add_(0, idx, torch.ones_like(idx))   # (bincount would sync)
         tstart = torch.cumsum(counts, 0) - counts                       # first sorted position of every index value
         pos = torch.arange(N, device=dev) - tstart[sidx]                # position inside its group
         first = (pos % R) == 0                                          # row opens a piece
         piece = torch.cumsum(first.to(torch.int64), 0) - 1              # piece id of every sorted row
         P = (N + R - 1) // R + T                                        # upper bound on the number of pieces
-        ptr1 = torch.full((P + 1,), N, dtype=torch.int32, device=dev)   # unused pieces are empty ([N, N))
+        ptr1 = torch.full((P + 2,), N, dtype=torch.int32, device=dev)   # unused pieces are empty ([N, N)); slot P+1 is a dump
         rows = torch.arange(N, device=dev, dtype=torch.int32)
-        ptr1[piece[first]] = rows[first]
+        ptr1.scatter_(0, torch.where(first, piece, torch.full_like(piece, P + 1)), rows)   # (mask indexing would sync)
+        ptr1 = ptr1[:P + 1]
         part = torch.empty(P, C, dtype=torch.float32, device=dev)
         ops.segment_sum(dy.contiguous(), ptr1, perm, P, part, PREC_FP32)
         # pieces of one index value are consecutive: its first piece is the piece of its first sorted row
