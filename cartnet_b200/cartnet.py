@@ -400,8 +400,9 @@ class Scalar_head(nn.Module, _PrecisionMixin):
 
 
 class CartNet(nn.Module, _PrecisionMixin):
-    """Mirror of /root/reference/models/cartnet.py:14-73. `precision` ("fp32" | "bf16") is the only
-    addition: fp32 SIMT GEMMs (1e-5 parity) or bf16 tcgen05 GEMMs (2e-3 parity)."""
+    """Mirror of /root/reference/models/cartnet.py:14-73. `precision` ("fp32" | "bf16x3" | "tf32" | "bf16") is the only
+    addition: fp32 SIMT GEMMs (1e-5 parity), or tcgen05 GEMMs on bf16 pairs (2e-3 parity in training and eval mode) /
+    tf32 / bf16 operands (2e-3 in eval mode only)."""
 
     def __init__(self, dim_in: int, dim_rbf: int, num_layers: int, radius: float = 5.0, invariant: bool = False,
                  temperature: bool = True, use_envelope: bool = True, atom_types: bool = True, cholesky: bool = True,
@@ -422,4 +423,6 @@ class CartNet(nn.Module, _PrecisionMixin):
         for layer in self.layers:
             batch = layer(batch)
         pred, true = self.head(batch)
+        from .batch import DevicePrefetcher
+        DevicePrefetcher.run_pending()      # a waiting prefetcher issues its next batch behind this forward's launches
         return pred, true
