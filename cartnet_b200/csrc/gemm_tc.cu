@@ -70,6 +70,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -437,6 +438,8 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr int NP = TR::NP;
     const bool prefetch = (stages & 16) != 0;        // host flags folded into `stages`
     const bool uni_path = (stages & 32) != 0;        // gather0 rows that are equal over a warp's 32 rows are loaded once
+    const bool gpf = (stages & 192) != 0;            // L1 prefetch of the next block's gathered rows
+    const int gpf_dist = (stages & 128) ? 2 : 1;
     stages &= 15;
     constexpr int KBOX = 128 / TR::TMA_ES;           // TMA elements per 128-byte box row
     constexpr int A_STAGE_BYTES = NP * NT_A_PART_BYTES;
@@ -612,6 +615,19 @@ tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int c = c_begin; c < c_end; c += 32) {
                 const int col = n0 + c + sub_c;
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                // L1 prefetch of the NEXT column block's gathered row segments (one 128-byte line per row: lane = row): the
+                // first use of the gathered data is where these warps wait (ncu: 22 % of all stall samples on that one FADD)
+                if (gpf && epi_has<EPI>(EB_GATHER, epi.gather0 != nullptr) && row0 + lane < M) {
+                    const int cn = c + 32 * gpf_dist;
+                    if (cn < c_end) {
+                        if (!uni) prefetch_l1(epi.gather0 + (int64_t)i0v * epi.ldg + n0 + cn);
+                        prefetch_l1(epi.gather1 + (int64_t)i1v * epi.ldg + n0 + cn);
+                    }
+                    if (c == c_begin && gpf_dist == 2 && c + 32 < c_end) {
+                        if (!uni) prefetch_l1(epi.gather0 + (int64_t)i0v * epi.ldg + n0 + c + 32);
+                        prefetch_l1(epi.gather1 + (int64_t)i1v * epi.ldg + n0 + c + 32);
+                    }
+                }
                 float4 bias[NV];
 #pragma unroll
                 for (int h = 0; h < NV; ++h)
@@ -1017,6 +1033,10 @@ static int run_nt(const cartnet_gemm_t& d, cudaStream_t st, double* stats, int* 
     if (pf_env && m_tiles > units / n_tiles && (CG == 1 || d.K >= 512)) stages |= 16;
     const char* uni_str = getenv("CARTNET_NT_UNIFORM");             // "0": always one gather0 load per row (A/B)
     if (!uni_str || atoi(uni_str) != 0) stages |= 32;
+    const char* gpf_str = getenv("CARTNET_NT_GATHER_PREFETCH");     // L1 prefetch of the gathered rows, blocks ahead: "0" off, "1" (default), "2"
+    const int gpf_mode = gpf_str ? atoi(gpf_str) : 1;               // first edge Linear at ADP-64: 0.812 / 0.774 / 0.781 ms
+    if (gpf_mode == 1) stages |= 64;
+    if (gpf_mode == 2) stages |= 128;
     int mask = 0;
     if (stats) mask |= EB_STATS;
     if (d.bias) mask |= EB_BIAS;
